@@ -1,0 +1,70 @@
+// common.cuh — shared device helpers for the sm_100a kernels (torch-free).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dgs {
+
+// Op algebra of the reference: include/gspmm.h:13-14 (REDUCEOP / COMPUTEOP enum order is part of
+// the gspmm-fp pybind surface, src/gspmm-fp/gspmm.cc:31-42).  C_COPY = "no edge value" kernels.
+enum ReduceOp { R_SUM = 0, R_MAX = 1, R_MIN = 2, R_MEAN = 3 };
+enum ComputeOp { C_ADD = 0, C_SUB = 1, C_MUL = 2, C_DIV = 3, C_COPY = 4 };
+
+constexpr int kMaxDst = 8;  // output fan-out (local C + NVLink peers) of the fused column-shard epilogue
+
+// MAX/MIN identities exactly as the reference: (float)INT_MIN / (float)INT_MAX, include/gspmm.h:133-146.
+template <int RED> __device__ __forceinline__ float reduce_identity() {
+  if (RED == R_MAX) return -2147483648.0f;
+  if (RED == R_MIN) return 2147483648.0f;
+  return 0.0f;
+}
+
+// COMPUTE::compute(a = edge value, b = feature), src/gspmm-fp/gspmm.h:53-79 (Sub = b - a, Div = b / a).
+template <int COMP> __device__ __forceinline__ float compute_op(float a, float b) {
+  if (COMP == C_ADD) return a + b;
+  if (COMP == C_SUB) return b - a;
+  if (COMP == C_MUL) return a * b;
+  if (COMP == C_DIV) return b / a;
+  return b;
+}
+
+// smallest idx in [0, n) with a[idx] > x (a ascending, a[n-1] > x guaranteed by the caller)
+__device__ __forceinline__ int upper_bound_i32(const int *__restrict__ a, int n, int x) {
+  int lo = 0, hi = n - 1;  // answer in [lo, hi]
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) > x) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// Row that owns nnz position p: rowptr[r] <= p < rowptr[r+1]; skips empty rows
+// (same contract as findRow / binary_search_segment_number, src/util/cuda_util.cuh:53-89,167-174).
+__device__ __forceinline__ int row_of_nnz(const int *__restrict__ rowptr, int M, int p) {
+  return upper_bound_i32(rowptr, M + 1, p) - 1;
+}
+
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using f = float;  using i = int;  };
+template <> struct VecT<2> { using f = float2; using i = int2; };
+template <> struct VecT<4> { using f = float4; using i = int4; };
+
+template <int VEC> __device__ __forceinline__ void ld_vec(float (&d)[VEC], const float *p) {
+  if (VEC == 4) { float4 t = __ldg(reinterpret_cast<const float4 *>(p)); d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w; }
+  else if (VEC == 2) { float2 t = __ldg(reinterpret_cast<const float2 *>(p)); d[0] = t.x; d[1] = t.y; }
+  else d[0] = __ldg(p);
+}
+
+template <int VEC> __device__ __forceinline__ void st_vec_cs(float *p, const float (&s)[VEC]) {
+  if (VEC == 4) __stcs(reinterpret_cast<float4 *>(p), make_float4(s[0], s[1], s[2], s[3]));
+  else if (VEC == 2) __stcs(reinterpret_cast<float2 *>(p), make_float2(s[0], s[1]));
+  else __stcs(p, s[0]);
+}
+
+template <int VEC> __device__ __forceinline__ void st_vec_cs(int *p, const int (&s)[VEC]) {
+  if (VEC == 4) __stcs(reinterpret_cast<int4 *>(p), make_int4(s[0], s[1], s[2], s[3]));
+  else if (VEC == 2) __stcs(reinterpret_cast<int2 *>(p), make_int2(s[0], s[1]));
+  else __stcs(p, s[0]);
+}
+
+}  // namespace dgs

@@ -1,0 +1,150 @@
+// spmm.cu — host dispatcher for the row-segment SpMM (geometry selection, segment sizing, workspace
+// carving, the two launches).  Replaces the launch logic of src/cuda/spmm_cuda.cu:14-253,
+// src/ge-spmm/gespmm.cc:29-134 and src/gspmm-fp/gspmm.cu:406-473 of the reference.
+#include <cstdio>
+#include "spmm.h"
+#include "spmm_rowseg.cuh"
+
+namespace dgs {
+
+#define DGS_DECL_LOOKUP(V, G) SpmmLaunchFn spmm_lookup_v##V##_g##G(int red, int comp, bool arg);
+DGS_DECL_LOOKUP(4, 4) DGS_DECL_LOOKUP(4, 8) DGS_DECL_LOOKUP(4, 16) DGS_DECL_LOOKUP(4, 32)
+DGS_DECL_LOOKUP(1, 4) DGS_DECL_LOOKUP(1, 8) DGS_DECL_LOOKUP(1, 16) DGS_DECL_LOOKUP(1, 32)
+
+template <bool ARG> static cudaError_t launch_fixup(int red, const SpmmArgs &a, int blocks, cudaStream_t s) {
+  switch (red) {
+  case R_MAX: spmm_fixup_kernel<R_MAX, ARG><<<blocks, 256, 0, s>>>(a); break;
+  case R_MIN: spmm_fixup_kernel<R_MIN, ARG><<<blocks, 256, 0, s>>>(a); break;
+  default: spmm_fixup_kernel<R_SUM, false><<<blocks, 256, 0, s>>>(a); break;
+  }
+  return cudaGetLastError();
+}
+
+int device_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int pow2_at_least(int x, int lo, int hi) {
+  int g = lo;
+  while (g < x && g < hi) g <<= 1;
+  return g;
+}
+
+// Lane-group geometry for feature width N.  vec4 needs 16-byte aligned rows everywhere.
+static void pick_geometry(int N, bool can_vec4, int *vec, int *G) {
+  if (can_vec4) {
+    *vec = 4;
+    *G = pow2_at_least((N + 3) / 4, 4, 32);   // N=16 -> 4, 32 -> 8, 64 -> 16, >=128 -> 32 (128-col panels)
+  } else {
+    *vec = 1;
+    *G = pow2_at_least(N, 4, 32);
+  }
+}
+
+// Segment length (nnz per lane group).  Depends only on (N, nnz, with_arg, #SMs) so that
+// spmm_workspace_bytes() and the launch agree.  Aim: ~8 segments per resident group (dynamic balance
+// through the block scheduler) while the partial workspace stays below kWorkspaceCap.
+static constexpr size_t kWorkspaceCap = 192u << 20;
+static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
+  const int64_t resident_groups = (int64_t)device_sm_count() * 3 * (kSpmmThreads / G);
+  int64_t chunk = (nnz + resident_groups * 8 - 1) / (resident_groups * 8);
+  if (chunk < 64) chunk = 64;
+  if (chunk > 8192) chunk = 8192;
+  const size_t per_chunk = (size_t)2 * N * 4 * (with_arg ? 2 : 1) + 4;
+  const int64_t min_for_ws = (int64_t)(((size_t)nnz * per_chunk + kWorkspaceCap - 1) / kWorkspaceCap);
+  if (chunk < min_for_ws) chunk = min_for_ws;
+  return (int)((chunk + kBatch - 1) / kBatch * kBatch);
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static void geometry_for(int N, int64_t nnz, bool with_arg, bool can_vec4, int *vec, int *G, int *chunk,
+                         int *num_chunks) {
+  pick_geometry(N, can_vec4, vec, G);
+  *chunk = pick_chunk(N, nnz, with_arg, *G);
+  *num_chunks = (int)((nnz + *chunk - 1) / *chunk);
+}
+
+size_t spmm_workspace_bytes(int N, int64_t nnz, bool with_arg) {
+  if (nnz <= 0 || N <= 0) return 256;
+  // the segment length differs between the vec4 and scalar geometries; size for the larger need
+  size_t need = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    int vec, G, chunk, nc;
+    geometry_for(N, nnz, with_arg, pass == 0, &vec, &G, &chunk, &nc);
+    size_t b = align_up((size_t)nc * 4, 256) + align_up((size_t)nc * 2 * N * 4, 256) * (with_arg ? 2 : 1);
+    if (b > need) need = b;
+  }
+  return need + 256;
+}
+
+cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (p.M <= 0 || p.N <= 0) return cudaSuccess;
+  if (p.n_dst < 1 || p.n_dst > kMaxDst) return cudaErrorInvalidValue;
+  const bool with_arg = p.E != nullptr;
+  if (with_arg && p.reduce != R_MAX && p.reduce != R_MIN) return cudaErrorInvalidValue;
+  const int comp = (p.val == nullptr) ? C_COPY : p.compute;
+
+  bool can_vec4 = (p.N % 4 == 0) && (p.ldb % 4 == 0) && (p.ldc % 4 == 0) && aligned16(p.B) && aligned16(workspace);
+  for (int d = 0; d < p.n_dst; d++) can_vec4 = can_vec4 && aligned16(p.dst[d]);
+  if (with_arg) can_vec4 = can_vec4 && aligned16(p.E) && (p.lde % 4 == 0);
+
+  SpmmArgs a;
+  a.M = p.M; a.N = p.N; a.nnz = (int)p.nnz;
+  a.rowptr = p.rowptr; a.col = p.col; a.val = p.val;
+  a.B = p.B; a.ldb = p.ldb; a.ldc = p.ldc;
+  a.E = p.E; a.lde = p.lde;
+  a.mean = (p.reduce == R_MEAN);
+  a.n_dst = p.n_dst;
+  for (int d = 0; d < kMaxDst; d++) a.dst[d] = d < p.n_dst ? p.dst[d] : nullptr;
+
+  int vec = 1, G = 32;
+  a.chunk = kBatch; a.num_chunks = 0;
+  a.part_val = nullptr; a.part_arg = nullptr; a.tail_row = nullptr;
+  if (p.nnz > 0) {
+    geometry_for(p.N, p.nnz, with_arg, can_vec4, &vec, &G, &a.chunk, &a.num_chunks);
+    const size_t tail_b = align_up((size_t)a.num_chunks * 4, 256);
+    const size_t part_b = align_up((size_t)a.num_chunks * 2 * p.N * 4, 256);
+    const size_t need = tail_b + part_b * (with_arg ? 2 : 1);
+    if (workspace == nullptr || workspace_bytes < need) return cudaErrorInvalidValue;
+    char *w = static_cast<char *>(workspace);
+    a.tail_row = reinterpret_cast<int *>(w);
+    a.part_val = reinterpret_cast<float *>(w + tail_b);
+    a.part_arg = with_arg ? reinterpret_cast<int *>(w + tail_b + part_b) : nullptr;
+
+    SpmmLaunchFn fn = nullptr;
+    const int key = vec * 100 + G;
+    switch (key) {
+    case 404: fn = spmm_lookup_v4_g4(p.reduce, comp, with_arg); break;
+    case 408: fn = spmm_lookup_v4_g8(p.reduce, comp, with_arg); break;
+    case 416: fn = spmm_lookup_v4_g16(p.reduce, comp, with_arg); break;
+    case 432: fn = spmm_lookup_v4_g32(p.reduce, comp, with_arg); break;
+    case 104: fn = spmm_lookup_v1_g4(p.reduce, comp, with_arg); break;
+    case 108: fn = spmm_lookup_v1_g8(p.reduce, comp, with_arg); break;
+    case 116: fn = spmm_lookup_v1_g16(p.reduce, comp, with_arg); break;
+    case 132: fn = spmm_lookup_v1_g32(p.reduce, comp, with_arg); break;
+    }
+    if (fn == nullptr) return cudaErrorInvalidValue;
+    const int gpb = kSpmmThreads / G;
+    dim3 grid((a.num_chunks + gpb - 1) / gpb, (p.N + G * vec - 1) / (G * vec));
+    cudaError_t e = fn(a, grid, stream);
+    if (e != cudaSuccess) return e;
+  }
+  const int64_t fold_threads = (int64_t)a.num_chunks * p.N;
+  const int64_t empty_threads = ((int64_t)p.M + 31) / 32 * 32;
+  const int64_t threads = fold_threads > empty_threads ? fold_threads : empty_threads;
+  const int blocks = (int)((threads + 255) / 256);
+  return with_arg ? launch_fixup<true>(p.reduce, a, blocks, stream) : launch_fixup<false>(p.reduce, a, blocks, stream);
+}
+
+}  // namespace dgs

@@ -1,0 +1,63 @@
+// spmm.h — internal C++ interface between the C ABI (cabi.cu) and the kernels.  Torch-free.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace dgs {
+
+struct SpmmProblem {
+  int M = 0, N = 0;
+  int64_t nnz = 0;
+  const int *rowptr = nullptr;
+  const int *col = nullptr;
+  const float *val = nullptr;   // null -> no edge value (copy_u / has_value = false)
+  const float *B = nullptr;
+  int64_t ldb = 0;
+  int n_dst = 1;
+  float *dst[8] = {nullptr};    // dst[0] = C; further entries = NVLink peers' C (column-shard epilogue)
+  int64_t ldc = 0;
+  int *E = nullptr;             // arg column index out (MAX / MIN only)
+  int64_t lde = 0;
+  int reduce = 0;               // dgs::ReduceOp
+  int compute = 2;              // dgs::ComputeOp (C_MUL)
+};
+
+size_t spmm_workspace_bytes(int N, int64_t nnz, bool with_arg);
+cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+int device_sm_count();
+
+struct SddmmProblem {
+  int M = 0, K = 0;
+  int64_t nnz = 0;
+  const int *rowptr = nullptr;  // CSR rows (null for COO)
+  const int *row = nullptr;     // COO row index per edge (null for CSR)
+  const int *col = nullptr;
+  const float *D1 = nullptr;    // [M, K] row-major, leading dim ld1
+  const float *D2 = nullptr;    // [*, K] row-major, leading dim ld2
+  int64_t ld1 = 0, ld2 = 0;
+  const int *E = nullptr;       // arg mask [M, K] (max/min backward), null otherwise
+  int mean = 0;                 // divide by the row degree (CSR only)
+  float *out = nullptr;         // [nnz]
+};
+cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream);
+
+// Masked SpMM of the max/min backward: out[j,v] = sum_p [E[idx[p],v] == j] val[p] * G[idx[p],v]
+struct SpmmMaskProblem {
+  int M = 0, N = 0;
+  int64_t nnz = 0;
+  const int *ptr = nullptr, *idx = nullptr;
+  const float *val = nullptr;
+  const float *G = nullptr;
+  const int *E = nullptr;
+  float *out = nullptr;
+};
+cudaError_t spmm_mask(const SpmmMaskProblem &p, cudaStream_t stream);
+
+size_t csr2csc_workspace_bytes(int M, int ncols, int64_t nnz);
+// colptr[ncols+1], row[nnz], val_t[nnz] (optional), perm[nnz] (optional): stable transpose
+cudaError_t csr2csc(int M, int ncols, int64_t nnz, const int *rowptr, const int *col, const float *val,
+                    int *colptr, int *row, float *val_t, int *perm, void *workspace, size_t workspace_bytes,
+                    cudaStream_t stream);
+
+}  // namespace dgs

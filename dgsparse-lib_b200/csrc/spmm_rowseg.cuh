@@ -1,0 +1,280 @@
+// spmm_rowseg.cuh — CSR SpMM / generalized SpMM for sm_100a: "each lane group owns a row segment".
+//
+// Replaces (behaviour, not code) the reference kernels
+//   csrspmm_seqreduce_rowbalance_kernel      include/cuda/spmm_cuda.cuh:10-55   (torch face, algorithm 0)
+//   csrspmm_rowcaching_rowbalance_kernel     src/ge-spmm/csrspmm_rowcaching.cu:11-119 (C ABI, N > 32)
+//   weighted/topo {Simple,Cache,CacheCoarsen}SPMMKernel   src/gspmm-fp/gspmm.cu:6-404
+//
+// Scheme
+//   * The nnz stream [0, nnz) is cut into equal SEGMENTS of `chunk` nonzeros (a multiple of 32).  A
+//     segment is owned by a GROUP of G lanes (G*VEC = the dense panel width handled per pass, e.g.
+//     N=64 -> 16 lanes x float4, two independent groups per warp; N=128 -> one warp x float4).  Load
+//     balance therefore never depends on the degree distribution (hub rows are simply split).
+//   * The group stages 32 (col, val) pairs at a time through shared memory (coalesced streaming
+//     loads, next batch prefetched into registers while the current one is consumed), then walks
+//     them: U dense rows B[col, panel] are requested back-to-back as 128-bit loads (one 128 B..512 B
+//     coalesced row slice per request) before any of them is consumed, so each group keeps U row
+//     gathers in flight.  Each lane owns VEC fixed output columns: accumulation over a row is
+//     serial in nnz order, exactly like the reference, and needs no cross-lane reduction.
+//   * Rows that end inside the segment are written straight to C.  A row cut by a segment boundary
+//     leaves a raw partial accumulator (head and/or tail slot of the segment) in a small workspace;
+//     spmm_fixup_kernel folds the partials of such a row IN SEGMENT ORDER (deterministic, preserves
+//     the first-extremum-wins arg rule) and also writes the 0 / -1 rows of empty rows.
+#pragma once
+#include <type_traits>
+#include "common.cuh"
+
+namespace dgs {
+
+struct SpmmArgs {
+  int M, N, nnz;
+  const int *rowptr;
+  const int *col;
+  const float *val;   // may be null iff COMP == C_COPY
+  const float *B;
+  int64_t ldb;
+  int64_t ldc;        // leading dimension of every destination in dst[]
+  int *E;             // arg column index (MAX/MIN), null otherwise
+  int64_t lde;
+  int chunk;          // nnz per segment, multiple of 32
+  int num_chunks;
+  int mean;           // divide the finished row by its nnz count
+  float *part_val;    // [num_chunks][2][N] raw partial accumulators: slot 0 = head, 1 = tail
+  int *part_arg;      // same shape, only with ARG
+  int *tail_row;      // [num_chunks] row whose tail partial lives in slot 1, or -1
+  int n_dst;          // 1 (local C) or the number of column-shard peers
+  float *dst[kMaxDst];
+};
+
+constexpr int kSpmmThreads = 256;
+constexpr int kBatch = 32;
+
+template <int RED, bool ARG, int VEC>
+__device__ __forceinline__ void reduce_step(float (&acc)[VEC], int (&arg)[VEC], const float (&x)[VEC], int c) {
+#pragma unroll
+  for (int v = 0; v < VEC; v++) {
+    if (RED == R_MAX) {          // include/cuda/spmm_cuda.cuh:38-42 + MAX macro include/gspmm.h:17
+      if (ARG) { if (acc[v] < x[v]) arg[v] = c; }
+      acc[v] = (acc[v] < x[v]) ? x[v] : acc[v];
+    } else if (RED == R_MIN) {   // MIN macro include/gspmm.h:16
+      if (ARG) { if (acc[v] > x[v]) arg[v] = c; }
+      acc[v] = (acc[v] < x[v]) ? acc[v] : x[v];
+    } else {
+      acc[v] += x[v];
+    }
+  }
+}
+
+template <int VEC, int G, int RED, int COMP, bool ARG, int U>
+__global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArgs a) {
+  constexpr int GPB = kSpmmThreads / G;  // groups (segments) per block
+  constexpr int PER = kBatch / G;        // staged entries per lane per batch
+  constexpr bool HAS_VAL = (COMP != C_COPY);
+  static_assert(kBatch % G == 0 && kBatch % U == 0, "bad tiling");
+
+  // +1 pad: groups of one warp read the same slot index of different rows -> distinct banks
+  __shared__ int s_col[GPB][kBatch + 1];
+  __shared__ float s_val[HAS_VAL ? GPB : 1][kBatch + 1];
+
+  const int grp = threadIdx.x / G;
+  const int gl = threadIdx.x % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (((threadIdx.x & 31) / G) * G));
+  const int chunk_id = blockIdx.x * GPB + grp;
+  if (chunk_id >= a.num_chunks) return;
+
+  const int lo = chunk_id * a.chunk;
+  const int hi = (a.nnz - lo <= a.chunk) ? a.nnz : lo + a.chunk;
+  const int colbase = blockIdx.y * (G * VEC) + gl * VEC;
+  const bool active = colbase < a.N;
+  const float *__restrict__ Bp = a.B + colbase;
+  const int *__restrict__ rowptr = a.rowptr;
+
+  int r = row_of_nnz(rowptr, a.M, lo);
+  int row_start = __ldg(rowptr + r);
+  int row_end = __ldg(rowptr + r + 1);
+
+  float acc[VEC];
+  int arg[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; v++) { acc[v] = reduce_identity<RED>(); arg[v] = -1; }
+
+  auto store_partial = [&](int slot) {
+    const size_t off = ((size_t)chunk_id * 2 + slot) * a.N + colbase;
+    if (VEC == 4) {
+      *reinterpret_cast<float4 *>(a.part_val + off) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      if (ARG) *reinterpret_cast<int4 *>(a.part_arg + off) = make_int4(arg[0], arg[1], arg[2], arg[3]);
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; v++) { a.part_val[off + v] = acc[v]; if (ARG) a.part_arg[off + v] = arg[v]; }
+    }
+  };
+
+  // row r has been consumed up to row_end (<= hi)
+  auto finish_row = [&]() {
+    if (active) {
+      if (row_start >= lo) {  // the whole row lies inside this segment: final result
+        float o[VEC];
+        const float deg = (float)(row_end - row_start);
+#pragma unroll
+        for (int v = 0; v < VEC; v++) o[v] = a.mean ? acc[v] / deg : acc[v];
+        const size_t off = (size_t)r * a.ldc + colbase;
+        for (int d = 0; d < a.n_dst; d++) st_vec_cs<VEC>(a.dst[d] + off, o);
+        if (ARG) st_vec_cs<VEC>(a.E + (size_t)r * a.lde + colbase, arg);
+      } else {
+        store_partial(0);     // the row began in an earlier segment: head partial
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; v++) { acc[v] = reduce_identity<RED>(); arg[v] = -1; }
+  };
+
+  auto advance_to = [&](int pos) {  // next non-empty row; pos is the first nnz not yet consumed
+    r += 1;
+    row_start = row_end;
+    row_end = __ldg(rowptr + r + 1);
+    if (row_end <= pos) {           // run of empty rows: jump
+      r = row_of_nnz(rowptr, a.M, pos);
+      row_start = __ldg(rowptr + r);
+      row_end = __ldg(rowptr + r + 1);
+    }
+  };
+
+  int creg[PER];
+  float vreg[PER];
+  auto prefetch = [&](int base) {
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const int idx = base + gl + k * G;
+      const bool ok = idx < hi;
+      creg[k] = ok ? __ldcs(a.col + idx) : 0;   // col 0 keeps the speculative B load in bounds
+      if (HAS_VAL) vreg[k] = ok ? __ldcs(a.val + idx) : 0.0f;
+    }
+  };
+  prefetch(lo);
+
+  // one nnz: close the previous row if pos crossed its end, then fold compute(val, B-row) into acc
+  auto fold = [&](int pos, int j, int c, const float (&bv)[VEC]) {
+    if (pos >= row_end) { finish_row(); advance_to(pos); }
+    float x[VEC];
+    const float ev = HAS_VAL ? s_val[grp][j] : 1.0f;
+#pragma unroll
+    for (int v = 0; v < VEC; v++) x[v] = compute_op<COMP>(ev, bv[v]);
+    reduce_step<RED, ARG, VEC>(acc, arg, x, c);
+  };
+
+  for (int base = lo; base < hi; base += kBatch) {
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      s_col[grp][gl + k * G] = creg[k];
+      if (HAS_VAL) s_val[grp][gl + k * G] = vreg[k];
+    }
+    __syncwarp(gmask);
+    prefetch(base + kBatch);
+    if (hi - base >= kBatch) {
+      // full batch: U row gathers in flight before the first one is consumed
+#pragma unroll 1
+      for (int j0 = 0; j0 < kBatch; j0 += U) {
+        float b[U][VEC];
+        int cc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          cc[u] = s_col[grp][j0 + u];
+          if (active) ld_vec<VEC>(b[u], Bp + (size_t)cc[u] * a.ldb);
+          else {
+#pragma unroll
+            for (int v = 0; v < VEC; v++) b[u][v] = 0.0f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) fold(base + j0 + u, j0 + u, cc[u], b[u]);
+      }
+    } else {
+      // ragged last batch of the last segment
+#pragma unroll 1
+      for (int j = 0; j < hi - base; j++) {
+        float b[VEC];
+        const int c = s_col[grp][j];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) b[v] = 0.0f;
+        if (active) ld_vec<VEC>(b, Bp + (size_t)c * a.ldb);
+        fold(base + j, j, c, b);
+      }
+    }
+    __syncwarp(gmask);
+  }
+
+  int tail = -1;
+  if (row_end == hi) {
+    finish_row();
+  } else if (row_start >= lo) {   // row continues into the next segment: tail partial, this group owns the row
+    if (active) store_partial(1);
+    tail = r;
+  } else {                        // row spans the whole segment
+    if (active) store_partial(0);
+  }
+  if (gl == 0 && blockIdx.y == 0) a.tail_row[chunk_id] = tail;
+}
+
+// Folds the partials of rows cut by segment boundaries (one thread per (segment, column)), in segment
+// order, and writes empty rows (0 and E = -1: include/cuda/spmm_cuda.cuh:49-53, src/gspmm-fp/gspmm.cu:222).
+template <int RED, bool ARG>
+__global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_fold = (int64_t)a.num_chunks * a.N;
+  if (t < n_fold) {
+    const int g = (int)(t / a.N);
+    const int c = (int)(t % a.N);
+    const int r = a.tail_row[g];
+    if (r >= 0) {
+      const int start = __ldg(a.rowptr + r), end = __ldg(a.rowptr + r + 1);
+      const int g_last = (end - 1) / a.chunk;
+      float acc = a.part_val[((size_t)g * 2 + 1) * a.N + c];
+      int arg = ARG ? a.part_arg[((size_t)g * 2 + 1) * a.N + c] : -1;
+      for (int gg = g + 1; gg <= g_last; gg++) {
+        const float x = a.part_val[((size_t)gg * 2) * a.N + c];
+        if (RED == R_MAX) {
+          if (ARG) { if (acc < x) arg = a.part_arg[((size_t)gg * 2) * a.N + c]; }
+          acc = (acc < x) ? x : acc;
+        } else if (RED == R_MIN) {
+          if (ARG) { if (acc > x) arg = a.part_arg[((size_t)gg * 2) * a.N + c]; }
+          acc = (acc < x) ? acc : x;
+        } else {
+          acc += x;
+        }
+      }
+      if (a.mean) acc = acc / (float)(end - start);
+      for (int d = 0; d < a.n_dst; d++) a.dst[d][(size_t)r * a.ldc + c] = acc;
+      if (ARG) a.E[(size_t)r * a.lde + c] = arg;
+    }
+  }
+  // empty rows: one warp scans 32 rows, then writes the zero rows cooperatively
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = t >> 5;
+  const int64_t row0 = warp * 32;
+  if (row0 < a.M) {
+    const int row = (int)row0 + lane;
+    bool empty = false;
+    if (row < a.M) empty = __ldg(a.rowptr + row) == __ldg(a.rowptr + row + 1);
+    unsigned m = __ballot_sync(0xffffffffu, empty);
+    while (m) {
+      const int rr = (int)row0 + (__ffs(m) - 1);
+      m &= m - 1;
+      for (int c = lane; c < a.N; c += 32) {
+        for (int d = 0; d < a.n_dst; d++) a.dst[d][(size_t)rr * a.ldc + c] = 0.0f;
+        if (ARG) a.E[(size_t)rr * a.lde + c] = -1;
+      }
+    }
+  }
+}
+
+// host-side launcher of one (VEC, G, RED, COMP, ARG) instance; defined in spmm_inst_*.cu
+using SpmmLaunchFn = cudaError_t (*)(const SpmmArgs &, dim3 grid, cudaStream_t);
+
+template <int VEC, int G, int RED, int COMP, bool ARG>
+cudaError_t launch_spmm_rowseg(const SpmmArgs &a, dim3 grid, cudaStream_t s) {
+  constexpr int U = (VEC == 4) ? 8 : 8;
+  spmm_rowseg_kernel<VEC, G, RED, COMP, ARG, U><<<grid, kSpmmThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace dgs
