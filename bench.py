@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload reddit64|products128|arxiv256]
+
+Workload (N=1): config 2 — SpMM sum on a reddit-like CSR (232 965 x 232 965, 114 615 892 nnz, synthetic,
+SURVEY.md §8d), feat = 64, fp32, edge values present.  A step = one pass of the hot path (the row-segment
+SpMM kernel + its fix-up kernel) over the whole matrix.  Metric: GFLOP/s = 2*nnz*N / t (the reference's
+convention, example/ge-spmm/spmm.cu:213-215), with the achieved HBM GB/s (algorithmic bytes / t) beside it.
+
+N>1 (torchrun, one rank per GPU): the feature axis is sharded — every rank holds the replicated CSR and a
+64-column panel of B (total feat = 64*N; N=8 is config 5), computes its panel of C and makes it visible on
+every rank (fused peer-store epilogue over NVLink + a one-int NCCL barrier, or an NCCL allgather when
+peer mapping is unavailable).  Per-GPU work is fixed -> "weak".  value = 2*nnz*64*N / max-over-ranks time.
+
+--impl reference: the reference's own CPU implementation of the path (spmm_reference_host from
+oracle/_ref when it was built from /root/reference, else the oracle port) on the host cores, rank 0 only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "dgsparse-lib_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+FEAT_PER_GPU = 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="reddit64", choices=["reddit64", "products128", "arxiv256"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debug only; default 1.0)")
+    ap.add_argument("--mode", default=None, choices=[None, "peer", "nccl"], help="N>1 exchange (default: peer)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes_spmm(M, nnz, N, k_touched, has_value, with_arg=False):
+    """rowptr + col + val + each referenced B row once + C (+ E for max/min)."""
+    return 4 * (M + 1) + 4 * nnz + (4 * nnz if has_value else 0) + 4 * k_touched * N + 4 * M * N + (4 * M * N if with_arg else 0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(name, scale):
+    from tools import graphs
+    graphs.build()
+    if name == "reddit64":
+        rowptr, col = graphs.reddit_like(scale)
+        return dict(name="reddit-like synthetic CSR (lognormal degrees, uniform columns, seed 20240001)", rowptr=rowptr,
+                    col=col, N=64, op="spmm_sum", has_value=True)
+    if name == "products128":
+        rowptr, col = graphs.products_like(scale)
+        return dict(name="ogbn-products-like synthetic CSR (power-law degrees, seed 20240002)", rowptr=rowptr, col=col,
+                    N=128, op="gspmm_u_mul_e_max", has_value=True)
+    rowptr, col = graphs.arxiv_like(scale)
+    return dict(name="ogbn-arxiv-like synthetic CSR (seed 20240003)", rowptr=rowptr, col=col, N=256, op="sddmm_csr",
+                has_value=False)
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(wl, steps, warmup, budget_s=12.0):
+    """Times the reference's CPU path on a bounded sample.  -> (gflops, info dict)."""
+    from oracle import oracle
+    from tools import graphs
+    oracle.build()
+    rowptr, col, N = wl["rowptr"], wl["col"], wl["N"]
+    M = rowptr.size - 1
+    cores = len(os.sched_getaffinity(0))
+    val = graphs.uniform(col.size, 1)
+    B = graphs.uniform(M * N, 2).reshape(M, N)
+    have_ref = oracle.ref_lib() is not None
+    if have_ref:
+        kind = "reference"
+
+        def run(r0, r1):
+            oracle.ref_spmm_host_threads(rowptr, col, val, B, threads=cores, rows=(r0, r1))
+    else:
+        kind = "port"
+        oracle.set_num_threads(cores)
+
+        def run(r0, r1):
+            oracle.spmm(rowptr[r0:r1 + 1] - rowptr[r0], col[rowptr[r0]:rowptr[r1]], val[rowptr[r0]:rowptr[r1]], B)
+    # probe on ~1/128 of the rows, then size the sample to the budget
+    probe_rows = max(64, M // 128)
+    run(0, probe_rows)
+    t0 = time.perf_counter(); run(0, probe_rows); tp = time.perf_counter() - t0
+    rate = int(rowptr[probe_rows]) / max(tp, 1e-6)                      # nnz / s
+    total_steps = max(1, steps + warmup)
+    sample_nnz = min(int(col.size), int(rate * budget_s / total_steps))
+    r1 = int(np.searchsorted(rowptr, sample_nnz, side="right") - 1)
+    r1 = min(max(r1, probe_rows), M)
+    nnz_s = int(rowptr[r1])
+    for _ in range(warmup):
+        run(0, r1)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); run(0, r1); ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    gflops = 2.0 * nnz_s * N / t / 1e9
+    info = {"value": gflops, "unit": "GFLOP/s", "cores": cores, "kind": kind,
+            "sample": f"rows [0,{r1}) of the same CSR ({nnz_s} nnz = {100.0 * nnz_s / col.size:.1f}% of the workload), "
+                      f"full B [{M},{N}], {steps} timed passes, row blocks spread over {cores} host threads",
+            "ms_per_sample": t * 1e3}
+    return gflops, info
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        wl = make_workload(args.workload, args.scale)
+        gflops, info = cpu_reference_run(wl, args.steps, args.warmup, budget_s=60.0)
+        M, nnz = wl["rowptr"].size - 1, wl["col"].size
+        line = {"impl": "reference", "metric": "spmm_gflops", "value": gflops, "unit": "GFLOP/s", "n_gpus": n_gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_sample"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{wl['op']} on {wl['name']}, M=K={M}, nnz={nnz}, feat={wl['N']}, fp32; "
+                                       f"CPU reference (spmm_reference_host, example/util/sp_util.hpp:62-84) on a bounded row sample"},
+                "cpu_baseline": info,
+                "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import dgsparse  # noqa: F401
+    import dgsparse._lib as L
+    import dgsparse._kernels as K
+    from dgsparse.distributed import ColumnShardedSpMM
+    from tools import graphs
+
+    wl = make_workload(args.workload, args.scale)
+    rowptr, col, N = wl["rowptr"], wl["col"], wl["N"]
+    M, nnz = rowptr.size - 1, int(col.size)
+    k_touched = int(np.unique(col).size) if nnz < 5e8 else M
+    val = graphs.uniform(nnz, 1) if wl["has_value"] else None
+    hbm_peak, peak_src = peaks()
+
+    rp, cc = torch.from_numpy(rowptr).to(dev), torch.from_numpy(col).to(dev)
+    vv = torch.from_numpy(val).to(dev) if val is not None else None
+    gen = torch.Generator(dev).manual_seed(1234 + rank)
+
+    extra = {}
+    if wl["op"] == "sddmm_csr":
+        D1 = torch.rand(M, N, device=dev, generator=gen)
+        D2 = torch.rand(M, N, device=dev, generator=gen)
+        out = torch.empty(1, nnz, device=dev)
+
+        def step():
+            L.check(L.lib.dgs_sddmm_csr(M, N, nnz, rp.data_ptr(), cc.data_ptr(), D1.data_ptr(), N, D2.data_ptr(), N,
+                                        None, 0, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "sddmm")
+        flop = 2.0 * nnz * N
+        alg_bytes = 4 * (M + 1) + 4 * nnz + 4 * M * N + 4 * k_touched * N + 4 * nnz
+        launches_per_step, main_id = 1, 3
+        mode = "replicas"
+    else:
+        reduce = L.MAX if "max" in wl["op"] else L.SUM
+        B = torch.rand(M, N, device=dev, generator=gen)
+        sh = ColumnShardedSpMM(rp, cc, vv, N, reduce=reduce, compute=L.MUL, mode=args.mode)
+        mode = sh.mode
+
+        def step():
+            sh(B)
+        flop = 2.0 * nnz * N * world
+        alg_bytes = algorithmic_bytes_spmm(M, nnz, N, k_touched, vv is not None)
+        launches_per_step, main_id = 2, 1
+        if world > 1:
+            extra["comm_bytes_in_per_rank"] = 4 * M * N * (world - 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- warm-up, then EXACTLY K timed steps ----------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.lib.dgs_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    ids = (ctypes.c_int * (4 * args.steps + 8))()
+    ms = (ctypes.c_float * (4 * args.steps + 8))()
+    nrec = L.lib.dgs_profile_collect(len(ids), ids, ms)
+    L.lib.dgs_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    kern_ms = [ms[i] for i in range(nrec) if ids[i] == main_id]
+    fix_ms = [ms[i] for i in range(nrec) if ids[i] == 2]
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = flop / (ms_per_step * 1e-3) / 1e9
+
+    # --- e2e: the same op through the HOST-pointer C-ABI call, H2D + D2H inside the timed region -------
+    e2e = None
+    if not args.no_e2e and wl["op"] != "sddmm_csr":
+        hp = lambda a: torch.from_numpy(a).pin_memory()
+        h_rp, h_cc = hp(rowptr), hp(col)
+        h_val = hp(val) if val is not None else None
+        h_B = B.cpu().pin_memory()
+        h_C = torch.empty(M, N, dtype=torch.float32).pin_memory()
+        red = L.MAX if "max" in wl["op"] else L.SUM
+
+        def e2e_step():
+            L.check(L.lib.dgs_spmm_csr_host(M, M, N, nnz, h_rp.data_ptr(), h_cc.data_ptr(),
+                                            h_val.data_ptr() if h_val is not None else None, h_B.data_ptr(),
+                                            h_C.data_ptr(), None, red, L.MUL), "dgs_spmm_csr_host")
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        ksteps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            e2e_step()
+        barrier()
+        te = torch.tensor([(time.perf_counter() - t0) / ksteps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = 4 * (M + 1) + 4 * nnz + (4 * nnz if val is not None else 0) + 4 * M * N
+        e2e = {"value": flop / float(te.item()) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4 * M * N, "ms_per_step": float(te.item()) * 1e3, "steps": ksteps,
+               "api": "dgs_spmm_csr_host (include/dgsparse_b200.h): pinned host CSR + B in, C out, every step"}
+
+    if rank == 0:
+        k_avg = sum(kern_ms) / max(1, len(kern_ms)) if kern_ms else ms_per_step
+        achieved = alg_bytes / (k_avg * 1e-3) / 1e9
+        line = {
+            "metric": "spmm_gflops" if wl["op"] != "sddmm_csr" else "sddmm_gflops",
+            "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl['op']} on {wl['name']}, M=K={M}, nnz={nnz}, feat={N} per GPU "
+                                   f"({N * world} total), fp32, edge values {'present' if vv is not None else 'absent'}",
+                       "parallelism": f"feature-axis column shard x{world}, CSR replicated, exchange={mode}",
+                       "l2": "no flush: inputs per step (%.0f MB) exceed the 126 MB L2" % (alg_bytes / 1e6)},
+            "achieved_hbm_gbs": alg_bytes * (world) / (ms_per_step * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "spmm_rowseg_kernel" if main_id == 1 else "sddmm_kernel",
+                         "kernel_ms_avg": k_avg, "fixup_ms_avg": (sum(fix_ms) / len(fix_ms)) if fix_ms else None,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "gather_bytes_per_launch": 4.0 * nnz * N,
+                         "note": "gathered B rows (nnz*N*4 B) are served by L2, see DESIGN.md"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        line.update(extra)
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline and wl["op"] != "sddmm_csr":
+            try:
+                _, info = cpu_reference_run(wl, steps=2, warmup=1, budget_s=12.0)
+                line["cpu_baseline"] = info
+            except Exception as ex:  # the checker is optional at bench time, the product is not
+                line["cpu_baseline"] = {"error": str(ex)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

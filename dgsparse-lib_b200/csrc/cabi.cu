@@ -1,0 +1,337 @@
+// cabi.cu — the C ABI of libdgsparse_b200.so: include/dgsparse.h (legacy dgSPARSE symbols) and
+// include/dgsparse_b200.h (extended, stream-taking).  No torch types anywhere.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <cuda.h>
+#include "../../include/dgsparse.h"
+#include "../../include/dgsparse_b200.h"
+#include "common.cuh"
+#include "spmm.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(cudaError_t e, const char *where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+  return (int)e;
+}
+int ok_or(cudaError_t e, const char *where) {
+  if (e == cudaSuccess) return 0;
+  return fail(e, where);
+}
+
+// Grow-only device scratch for the legacy (workspace-less) entry points; one per device, used on
+// stream 0 only, so reuse across calls is ordered by the stream.
+struct Scratch {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+};
+std::mutex g_mu;
+Scratch g_scratch[64];
+
+cudaError_t legacy_scratch(size_t need, void **out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lk(g_mu);
+  Scratch &s = g_scratch[dev];
+  if (s.bytes < need) {
+    if (s.ptr) {
+      if ((e = cudaStreamSynchronize(0)) != cudaSuccess) return e;
+      cudaFree(s.ptr);
+      s.ptr = nullptr; s.bytes = 0;
+    }
+    size_t want = need + need / 4 + (1u << 20);
+    if ((e = cudaMalloc(&s.ptr, want)) != cudaSuccess) return e;
+    s.bytes = want;
+  }
+  *out = s.ptr;
+  return cudaSuccess;
+}
+
+void legacy_report(int rc, const char *fn) {
+  if (rc != 0) fprintf(stderr, "[dgsparse_b200] %s failed: %s\n", fn, g_err);
+}
+
+// nnz of a device CSR when the caller does not pass it (legacy spmm_cuda): rowptr[m] via a 4-byte copy.
+cudaError_t read_nnz(const int *rowptr, int m, int *nnz) {
+  return cudaMemcpy(nnz, rowptr + m, sizeof(int), cudaMemcpyDeviceToHost);
+}
+
+// ---- column-major SpMM (gespmmCsrSpMM with transpose_BC = false) ---------------------------------
+// B[K,N] and C[M,N] column-major (ldB = K, ldC = M), src/ge-spmm/csrspmm_non_transpose.cu:479-600.
+// One thread per output element, rows fastest so that C stores and rowptr loads coalesce.
+__global__ void __launch_bounds__(256) spmm_colmajor_kernel(int M, int N, int K, const int *__restrict__ rowptr,
+                                                            const int *__restrict__ col, const float *__restrict__ val,
+                                                            const float *__restrict__ B, float *__restrict__ C) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (r >= M) return;
+  const float *Bn = B + (size_t)n * K;
+  float acc = 0.0f;
+  const int end = __ldg(rowptr + r + 1);
+  for (int p = __ldg(rowptr + r); p < end; p++) acc += (val ? __ldg(val + p) : 1.0f) * __ldg(Bn + __ldg(col + p));
+  C[(size_t)n * M + r] = acc;
+}
+
+// ---- edge softmax --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) edge_softmax_kernel(int M, int head, const int *__restrict__ rowptr,
+                                                           const float *__restrict__ v, float *__restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int s = __ldg(rowptr + warp), e = __ldg(rowptr + warp + 1);
+  for (int h = 0; h < head; h++) {
+    float mx = -INFINITY;
+    for (int p = s + lane; p < e; p += 32) mx = fmaxf(mx, v[(size_t)p * head + h]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.0f;
+    for (int p = s + lane; p < e; p += 32) sum += expf(v[(size_t)p * head + h] - mx);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int p = s + lane; p < e; p += 32) out[(size_t)p * head + h] = expf(v[(size_t)p * head + h] - mx) / sum;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int dgs_version(void) { return 100; }
+int dgs_cuda_version(void) { return CUDA_VERSION; }
+const char *dgs_last_error(void) { return g_err; }
+int dgs_sm_count(void) { return dgs::device_sm_count(); }
+
+size_t dgs_spmm_workspace_bytes(int N, int64_t nnz, int with_arg) {
+  return dgs::spmm_workspace_bytes(N, nnz, with_arg != 0);
+}
+
+int dgs_spmm_csr_multi(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
+                       int64_t ldb, int n_dst, float *const *dst, int64_t ldc, int reduce, int compute, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+  if (n_dst < 1 || n_dst > dgs::kMaxDst || dst == nullptr) return fail(cudaErrorInvalidValue, "dgs_spmm_csr_multi(n_dst)");
+  dgs::SpmmProblem p;
+  p.M = M; p.N = N; p.nnz = nnz; p.rowptr = rowptr; p.col = col; p.val = val; p.B = B; p.ldb = ldb;
+  p.n_dst = n_dst;
+  for (int d = 0; d < n_dst; d++) p.dst[d] = dst[d];
+  p.ldc = ldc; p.reduce = reduce; p.compute = compute;
+  return ok_or(dgs::spmm_csr(p, workspace, workspace_bytes, (cudaStream_t)stream), "dgs_spmm_csr_multi");
+}
+
+int dgs_spmm_csr(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
+                 int64_t ldb, float *C, int64_t ldc, int *E, int64_t lde, int reduce, int compute, void *workspace,
+                 size_t workspace_bytes, void *stream) {
+  dgs::SpmmProblem p;
+  p.M = M; p.N = N; p.nnz = nnz; p.rowptr = rowptr; p.col = col; p.val = val; p.B = B; p.ldb = ldb;
+  p.n_dst = 1; p.dst[0] = C; p.ldc = ldc; p.E = E; p.lde = lde; p.reduce = reduce; p.compute = compute;
+  if (compute == DGS_MASKMUL) return fail(cudaErrorInvalidValue, "dgs_spmm_csr(compute): use dgs_spmm_csr_mask");
+  return ok_or(dgs::spmm_csr(p, workspace, workspace_bytes, (cudaStream_t)stream), "dgs_spmm_csr");
+}
+
+int dgs_spmm_csr_mask(int M, int N, int64_t nnz, const int *ptr, const int *idx, const float *val, const float *G,
+                      int64_t ldg, const int *E, int64_t lde, float *out, int64_t ldo, void *workspace,
+                      size_t workspace_bytes, void *stream) {
+  dgs::SpmmProblem p;
+  p.M = M; p.N = N; p.nnz = nnz; p.rowptr = ptr; p.col = idx; p.val = val; p.B = G; p.ldb = ldg;
+  p.n_dst = 1; p.dst[0] = out; p.ldc = ldo; p.reduce = dgs::R_SUM; p.compute = dgs::C_MASK;
+  p.mask = E; p.ldm = lde;
+  return ok_or(dgs::spmm_csr(p, workspace, workspace_bytes, (cudaStream_t)stream), "dgs_spmm_csr_mask");
+}
+
+int dgs_sddmm_csr(int M, int K, int64_t nnz, const int *rowptr, const int *col, const float *D1, int64_t ld1,
+                  const float *D2, int64_t ld2, const int *E, int mean, float *out, void *stream) {
+  dgs::SddmmProblem p;
+  p.M = M; p.K = K; p.nnz = nnz; p.rowptr = rowptr; p.col = col; p.D1 = D1; p.D2 = D2; p.ld1 = ld1; p.ld2 = ld2;
+  p.E = E; p.mean = mean; p.out = out;
+  if (rowptr == nullptr) return fail(cudaErrorInvalidValue, "dgs_sddmm_csr(rowptr)");
+  return ok_or(dgs::sddmm(p, (cudaStream_t)stream), "dgs_sddmm_csr");
+}
+
+int dgs_sddmm_coo(int K, int64_t nnz, const int *row, const int *col, const float *D1, int64_t ld1, const float *D2,
+                  int64_t ld2, float *out, void *stream) {
+  dgs::SddmmProblem p;
+  p.M = 0; p.K = K; p.nnz = nnz; p.row = row; p.col = col; p.D1 = D1; p.D2 = D2; p.ld1 = ld1; p.ld2 = ld2; p.out = out;
+  if (row == nullptr) return fail(cudaErrorInvalidValue, "dgs_sddmm_coo(row)");
+  return ok_or(dgs::sddmm(p, (cudaStream_t)stream), "dgs_sddmm_coo");
+}
+
+size_t dgs_csr2csc_workspace_bytes(int M, int ncols, int64_t nnz) { return dgs::csr2csc_workspace_bytes(M, ncols, nnz); }
+
+int dgs_csr2csc(int M, int ncols, int64_t nnz, const int *rowptr, const int *col, const float *val, int *colptr,
+                int *row, float *val_t, int *perm, void *workspace, size_t workspace_bytes, void *stream) {
+  return ok_or(dgs::csr2csc(M, ncols, nnz, rowptr, col, val, colptr, row, val_t, perm, workspace, workspace_bytes,
+                            (cudaStream_t)stream), "dgs_csr2csc");
+}
+
+int dgs_edge_softmax(int M, int head, const int *rowptr, const float *values, float *out, void *stream) {
+  if (M <= 0 || head <= 0) return 0;
+  const int blocks = (int)(((int64_t)M * 32 + 255) / 256);
+  edge_softmax_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(M, head, rowptr, values, out);
+  return ok_or(cudaGetLastError(), "dgs_edge_softmax");
+}
+
+// ---- host-buffer entry points --------------------------------------------------------------------
+namespace {
+struct HostStage {
+  void *dev = nullptr;
+  size_t bytes = 0;
+  cudaStream_t stream = nullptr;
+  int device = -1;
+};
+thread_local HostStage g_stage;
+
+cudaError_t stage_reserve(size_t need) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  HostStage &s = g_stage;
+  if (s.device != dev) {
+    if (s.dev) { cudaFree(s.dev); s.dev = nullptr; s.bytes = 0; }
+    if (s.stream) { cudaStreamDestroy(s.stream); s.stream = nullptr; }
+    if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    s.device = dev;
+  }
+  if (s.bytes < need) {
+    if (s.dev) { cudaFree(s.dev); s.dev = nullptr; s.bytes = 0; }
+    if ((e = cudaMalloc(&s.dev, need)) != cudaSuccess) return e;
+    s.bytes = need;
+  }
+  return cudaSuccess;
+}
+inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+}  // namespace
+
+int dgs_spmm_csr_host(int M, int K, int N, int64_t nnz, const int *rowptr, const int *col, const float *val,
+                      const float *B, float *C, int *E, int reduce, int compute) {
+  if (M < 0 || K < 0 || N < 0 || nnz < 0) return fail(cudaErrorInvalidValue, "dgs_spmm_csr_host(sizes)");
+  const bool with_arg = E != nullptr;
+  const size_t b_rowptr = up256(4 * ((size_t)M + 1)), b_col = up256(4 * (size_t)nnz), b_val = val ? b_col : 0;
+  const size_t b_B = up256(4 * (size_t)K * N), b_C = up256(4 * (size_t)M * N), b_E = with_arg ? b_C : 0;
+  const size_t b_ws = up256(dgs::spmm_workspace_bytes(N, nnz, with_arg));
+  cudaError_t e = stage_reserve(b_rowptr + b_col + b_val + b_B + b_C + b_E + b_ws);
+  if (e != cudaSuccess) return fail(e, "dgs_spmm_csr_host(alloc)");
+  char *d = static_cast<char *>(g_stage.dev);
+  cudaStream_t s = g_stage.stream;
+  int *d_rowptr = (int *)d; d += b_rowptr;
+  int *d_col = (int *)d; d += b_col;
+  float *d_val = val ? (float *)d : nullptr; d += b_val;
+  float *d_B = (float *)d; d += b_B;
+  float *d_C = (float *)d; d += b_C;
+  int *d_E = with_arg ? (int *)d : nullptr; d += b_E;
+  void *d_ws = d;
+  if ((e = cudaMemcpyAsync(d_rowptr, rowptr, 4 * ((size_t)M + 1), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, "h2d rowptr");
+  if ((e = cudaMemcpyAsync(d_col, col, 4 * (size_t)nnz, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, "h2d col");
+  if (val && (e = cudaMemcpyAsync(d_val, val, 4 * (size_t)nnz, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, "h2d val");
+  if ((e = cudaMemcpyAsync(d_B, B, 4 * (size_t)K * N, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, "h2d B");
+  int rc = dgs_spmm_csr(M, N, nnz, d_rowptr, d_col, d_val, d_B, N, d_C, N, d_E, N, reduce, compute, d_ws, b_ws, s);
+  if (rc) return rc;
+  if ((e = cudaMemcpyAsync(C, d_C, 4 * (size_t)M * N, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e, "d2h C");
+  if (with_arg && (e = cudaMemcpyAsync(E, d_E, 4 * (size_t)M * N, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e, "d2h E");
+  return ok_or(cudaStreamSynchronize(s), "dgs_spmm_csr_host(sync)");
+}
+
+int dgs_sddmm_csr_host(int M, int Kdim, int ncols, int64_t nnz, const int *rowptr, const int *col, const float *D1,
+                       const float *D2, float *out) {
+  if (M < 0 || Kdim < 0 || ncols < 0 || nnz < 0) return fail(cudaErrorInvalidValue, "dgs_sddmm_csr_host(sizes)");
+  const size_t b_rowptr = up256(4 * ((size_t)M + 1)), b_col = up256(4 * (size_t)nnz);
+  const size_t b_D1 = up256(4 * (size_t)M * Kdim), b_D2 = up256(4 * (size_t)ncols * Kdim), b_out = b_col;
+  cudaError_t e = stage_reserve(b_rowptr + b_col + b_D1 + b_D2 + b_out);
+  if (e != cudaSuccess) return fail(e, "dgs_sddmm_csr_host(alloc)");
+  char *d = static_cast<char *>(g_stage.dev);
+  cudaStream_t s = g_stage.stream;
+  int *d_rowptr = (int *)d; d += b_rowptr;
+  int *d_col = (int *)d; d += b_col;
+  float *d_D1 = (float *)d; d += b_D1;
+  float *d_D2 = (float *)d; d += b_D2;
+  float *d_out = (float *)d;
+  if ((e = cudaMemcpyAsync(d_rowptr, rowptr, 4 * ((size_t)M + 1), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, "h2d rowptr");
+  if ((e = cudaMemcpyAsync(d_col, col, 4 * (size_t)nnz, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, "h2d col");
+  if ((e = cudaMemcpyAsync(d_D1, D1, 4 * (size_t)M * Kdim, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, "h2d D1");
+  if ((e = cudaMemcpyAsync(d_D2, D2, 4 * (size_t)ncols * Kdim, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, "h2d D2");
+  int rc = dgs_sddmm_csr(M, Kdim, nnz, d_rowptr, d_col, d_D1, Kdim, d_D2, Kdim, nullptr, 0, d_out, s);
+  if (rc) return rc;
+  if ((e = cudaMemcpyAsync(out, d_out, 4 * (size_t)nnz, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e, "d2h out");
+  return ok_or(cudaStreamSynchronize(s), "dgs_sddmm_csr_host(sync)");
+}
+
+// ---- peer memory (column-shard epilogue over NVLink) ---------------------------------------------
+int dgs_ipc_export(const void *dptr, void *handle64, int64_t *offset) {
+  typedef CUresult (*range_fn)(CUdeviceptr *, size_t *, CUdeviceptr);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || fn == nullptr) return fail(e != cudaSuccess ? e : cudaErrorNotSupported, "dgs_ipc_export(entry point)");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (((range_fn)fn)(&base, &size, (CUdeviceptr)dptr) != CUDA_SUCCESS) return fail(cudaErrorInvalidValue, "dgs_ipc_export(range)");
+  cudaIpcMemHandle_t h;
+  if ((e = cudaIpcGetMemHandle(&h, (void *)base)) != cudaSuccess) return fail(e, "dgs_ipc_export(handle)");
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  *offset = (int64_t)((CUdeviceptr)dptr - base);
+  return 0;
+}
+
+int dgs_ipc_open(const void *handle64, void **base) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  return ok_or(cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess), "dgs_ipc_open");
+}
+
+int dgs_ipc_close(void *base) { return ok_or(cudaIpcCloseMemHandle(base), "dgs_ipc_close"); }
+
+// ---- per-launch timing for bench.py's roofline leg -----------------------------------------------
+int dgs_profile_enable(int on) { return dgs::profile_enable(on != 0); }
+int dgs_profile_collect(int max_records, int *kernel_ids, float *ms) { return dgs::profile_collect(max_records, kernel_ids, ms); }
+
+// ---- legacy dgSPARSE symbols (include/dgsparse.h) ------------------------------------------------
+
+void gespmmCsrSpMM(const SpMatCsrDescr_t A, float *B, const int N, float *C, bool transpose_BC, gespmmAlg_t alg) {
+  (void)alg;  // every reference algorithm computes the same C; one kernel serves them all
+  int nnz = A.nnz;
+  if (nnz < 0) {
+    cudaError_t e = read_nnz(A.indptr, A.nrow, &nnz);
+    if (e != cudaSuccess) { legacy_report(fail(e, "gespmmCsrSpMM(read nnz)"), "gespmmCsrSpMM"); return; }
+  }
+  if (!transpose_BC) {
+    if (A.nrow <= 0 || N <= 0) return;
+    dim3 grid((A.nrow + 255) / 256, N);
+    spmm_colmajor_kernel<<<grid, 256, 0, 0>>>(A.nrow, N, A.ncol, A.indptr, A.indices, A.data, B, C);
+    legacy_report(ok_or(cudaGetLastError(), "gespmmCsrSpMM(colmajor)"), "gespmmCsrSpMM");
+    return;
+  }
+  const size_t need = dgs::spmm_workspace_bytes(N, nnz, false);
+  void *ws = nullptr;
+  cudaError_t e = legacy_scratch(need, &ws);
+  if (e != cudaSuccess) { legacy_report(fail(e, "gespmmCsrSpMM(scratch)"), "gespmmCsrSpMM"); return; }
+  legacy_report(dgs_spmm_csr(A.nrow, N, nnz, A.indptr, A.indices, A.data, B, N, C, N, nullptr, 0, DGS_SUM, DGS_MUL, ws,
+                             need, nullptr), "gespmmCsrSpMM");
+}
+
+void spmm_cuda(int m, int k, int *rowptr, int *colind, float *values, float *dense, float *out) {
+  SpMatCsrDescr_t A = {m, 0, -1, rowptr, colind, values};
+  gespmmCsrSpMM(A, dense, k, out, true, GESPMM_ALG_DEFAULT);
+}
+
+void spmm_cuda_no_edge_value(int m, int k, int *rowptr, int *colind, float *values, float *dense, float *out) {
+  (void)values;
+  spmm_cuda(m, k, rowptr, colind, nullptr, dense, out);
+}
+
+void sddmm_cuda_coo(int k, int nnz, int *rowind, int *colind, float *D1, float *D2, float *out) {
+  legacy_report(dgs_sddmm_coo(k, nnz, rowind, colind, D1, k, D2, k, out, nullptr), "sddmm_cuda_coo");
+}
+
+void sddmm_cuda_csr(int m, int k, int nnz, int *rowptr, int *colind, float *D1, float *D2, float *out) {
+  legacy_report(dgs_sddmm_csr(m, k, nnz, rowptr, colind, D1, k, D2, k, nullptr, 0, out, nullptr), "sddmm_cuda_csr");
+}
+
+void edge_softmax_cuda(int mrows, int head, int *rowptr, float *values, float *softmax) {
+  legacy_report(dgs_edge_softmax(mrows, head, rowptr, values, softmax, nullptr), "edge_softmax_cuda");
+}
+
+}  // extern "C"

@@ -8,7 +8,7 @@ namespace dgs {
 // Op algebra of the reference: include/gspmm.h:13-14 (REDUCEOP / COMPUTEOP enum order is part of
 // the gspmm-fp pybind surface, src/gspmm-fp/gspmm.cc:31-42).  C_COPY = "no edge value" kernels.
 enum ReduceOp { R_SUM = 0, R_MAX = 1, R_MIN = 2, R_MEAN = 3 };
-enum ComputeOp { C_ADD = 0, C_SUB = 1, C_MUL = 2, C_DIV = 3, C_COPY = 4 };
+enum ComputeOp { C_ADD = 0, C_SUB = 1, C_MUL = 2, C_DIV = 3, C_COPY = 4, C_MASK = 5 };  // C_MASK: multiply, masked by the forward's arg index
 
 constexpr int kMaxDst = 8;  // output fan-out (local C + NVLink peers) of the fused column-shard epilogue
 
@@ -23,7 +23,7 @@ template <int RED> __device__ __forceinline__ float reduce_identity() {
 template <int COMP> __device__ __forceinline__ float compute_op(float a, float b) {
   if (COMP == C_ADD) return a + b;
   if (COMP == C_SUB) return b - a;
-  if (COMP == C_MUL) return a * b;
+  if (COMP == C_MUL || COMP == C_MASK) return a * b;
   if (COMP == C_DIV) return b / a;
   return b;
 }
@@ -52,6 +52,12 @@ template <> struct VecT<4> { using f = float4; using i = int4; };
 template <int VEC> __device__ __forceinline__ void ld_vec(float (&d)[VEC], const float *p) {
   if (VEC == 4) { float4 t = __ldg(reinterpret_cast<const float4 *>(p)); d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w; }
   else if (VEC == 2) { float2 t = __ldg(reinterpret_cast<const float2 *>(p)); d[0] = t.x; d[1] = t.y; }
+  else d[0] = __ldg(p);
+}
+
+template <int VEC> __device__ __forceinline__ void ld_ivec(int (&d)[VEC], const int *p) {
+  if (VEC == 4) { int4 t = __ldg(reinterpret_cast<const int4 *>(p)); d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w; }
+  else if (VEC == 2) { int2 t = __ldg(reinterpret_cast<const int2 *>(p)); d[0] = t.x; d[1] = t.y; }
   else d[0] = __ldg(p);
 }
 

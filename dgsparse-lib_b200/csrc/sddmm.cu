@@ -34,11 +34,6 @@ struct SddmmArgs {
   int chunk, num_chunks;
 };
 
-template <int VEC> __device__ __forceinline__ void ld_ivec(int (&d)[VEC], const int *p) {
-  if (VEC == 4) { int4 t = __ldg(reinterpret_cast<const int4 *>(p)); d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w; }
-  else d[0] = __ldg(p);
-}
-
 // Reduce NV per-lane partials across the G lanes of a group.  On return the lane whose low
 // log2(G/NV) bits are zero holds, in v[0], the full sum of edge `edge_slot(gl)`.
 template <int G, int NV>
@@ -232,6 +227,7 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
   if (chunk > 4096) chunk = 4096;
   a.chunk = (int)((chunk + kSdBatch - 1) / kSdBatch * kSdBatch);
   a.num_chunks = (int)((p.nnz + a.chunk - 1) / a.chunk);
+  ProfileScope prof(3, stream);
   return vec4 ? launch_v<4>(G, a, coo, p.mean != 0 && !coo, mask && !coo, stream)
               : launch_v<1>(G, a, coo, p.mean != 0 && !coo, mask && !coo, stream);
 }

@@ -2,6 +2,7 @@
 // carving, the two launches).  Replaces the launch logic of src/cuda/spmm_cuda.cu:14-253,
 // src/ge-spmm/gespmm.cc:29-134 and src/gspmm-fp/gspmm.cu:406-473 of the reference.
 #include <cstdio>
+#include <vector>
 #include "spmm.h"
 #include "spmm_rowseg.cuh"
 
@@ -18,6 +19,50 @@ template <bool ARG> static cudaError_t launch_fixup(int red, const SpmmArgs &a, 
   default: spmm_fixup_kernel<R_SUM, false><<<blocks, 256, 0, s>>>(a); break;
   }
   return cudaGetLastError();
+}
+
+// ---- bench-only per-launch timing -----------------------------------------------------------------
+namespace {
+struct ProfRec { int id; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+int profile_enable(bool on) {
+  g_prof_on = on;
+  if (!on) {
+    for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+  }
+  return 0;
+}
+
+ProfileScope::ProfileScope(int kernel_id, cudaStream_t s) : slot(-1), stream(s) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.id = kernel_id;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+  slot = (int)g_prof.size() - 1;
+}
+
+ProfileScope::~ProfileScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].b, stream);
+}
+
+int profile_collect(int max_records, int *kernel_ids, float *ms) {
+  int n = 0;
+  for (auto &r : g_prof) {
+    cudaEventSynchronize(r.b);
+    float t = 0.0f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    if (n < max_records) { kernel_ids[n] = r.id; ms[n] = t; n++; }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return n;
 }
 
 int device_sm_count() {
@@ -93,17 +138,20 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   if (p.n_dst < 1 || p.n_dst > kMaxDst) return cudaErrorInvalidValue;
   const bool with_arg = p.E != nullptr;
   if (with_arg && p.reduce != R_MAX && p.reduce != R_MIN) return cudaErrorInvalidValue;
-  const int comp = (p.val == nullptr) ? C_COPY : p.compute;
+  const int comp = (p.compute == C_MASK) ? C_MASK : (p.val == nullptr) ? C_COPY : p.compute;
+  if (comp == C_MASK && (p.mask == nullptr || p.reduce != R_SUM || with_arg)) return cudaErrorInvalidValue;
 
   bool can_vec4 = (p.N % 4 == 0) && (p.ldb % 4 == 0) && (p.ldc % 4 == 0) && aligned16(p.B) && aligned16(workspace);
   for (int d = 0; d < p.n_dst; d++) can_vec4 = can_vec4 && aligned16(p.dst[d]);
   if (with_arg) can_vec4 = can_vec4 && aligned16(p.E) && (p.lde % 4 == 0);
+  if (comp == C_MASK) can_vec4 = can_vec4 && aligned16(p.mask) && (p.ldm % 4 == 0);
 
   SpmmArgs a;
   a.M = p.M; a.N = p.N; a.nnz = (int)p.nnz;
   a.rowptr = p.rowptr; a.col = p.col; a.val = p.val;
   a.B = p.B; a.ldb = p.ldb; a.ldc = p.ldc;
   a.E = p.E; a.lde = p.lde;
+  a.mask = p.mask; a.ldm = p.ldm;
   a.mean = (p.reduce == R_MEAN);
   a.n_dst = p.n_dst;
   for (int d = 0; d < kMaxDst; d++) a.dst[d] = d < p.n_dst ? p.dst[d] : nullptr;
@@ -137,13 +185,18 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
     if (fn == nullptr) return cudaErrorInvalidValue;
     const int gpb = kSpmmThreads / G;
     dim3 grid((a.num_chunks + gpb - 1) / gpb, (p.N + G * vec - 1) / (G * vec));
-    cudaError_t e = fn(a, grid, stream);
+    cudaError_t e;
+    {
+      ProfileScope prof(1, stream);
+      e = fn(a, grid, stream);
+    }
     if (e != cudaSuccess) return e;
   }
   const int64_t fold_threads = (int64_t)a.num_chunks * p.N;
   const int64_t empty_threads = ((int64_t)p.M + 31) / 32 * 32;
   const int64_t threads = fold_threads > empty_threads ? fold_threads : empty_threads;
   const int blocks = (int)((threads + 255) / 256);
+  ProfileScope prof(2, stream);
   return with_arg ? launch_fixup<true>(p.reduce, a, blocks, stream) : launch_fixup<false>(p.reduce, a, blocks, stream);
 }
 

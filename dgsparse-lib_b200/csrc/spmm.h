@@ -21,11 +21,23 @@ struct SpmmProblem {
   int64_t lde = 0;
   int reduce = 0;               // dgs::ReduceOp
   int compute = 2;              // dgs::ComputeOp (C_MUL)
+  const int *mask = nullptr;    // compute == C_MASK: the forward's arg tensor, row stride ldm
+  int64_t ldm = 0;
 };
 
 size_t spmm_workspace_bytes(int N, int64_t nnz, bool with_arg);
 cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int device_sm_count();
+
+// bench-only launch timing (see dgs_profile_enable in include/dgsparse_b200.h)
+int profile_enable(bool on);
+int profile_collect(int max_records, int *kernel_ids, float *ms);
+struct ProfileScope {   // RAII: records an event pair around the launches issued inside the scope
+  ProfileScope(int kernel_id, cudaStream_t s);
+  ~ProfileScope();
+  int slot;
+  cudaStream_t stream;
+};
 
 struct SddmmProblem {
   int M = 0, K = 0;
@@ -41,18 +53,6 @@ struct SddmmProblem {
   float *out = nullptr;         // [nnz]
 };
 cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream);
-
-// Masked SpMM of the max/min backward: out[j,v] = sum_p [E[idx[p],v] == j] val[p] * G[idx[p],v]
-struct SpmmMaskProblem {
-  int M = 0, N = 0;
-  int64_t nnz = 0;
-  const int *ptr = nullptr, *idx = nullptr;
-  const float *val = nullptr;
-  const float *G = nullptr;
-  const int *E = nullptr;
-  float *out = nullptr;
-};
-cudaError_t spmm_mask(const SpmmMaskProblem &p, cudaStream_t stream);
 
 size_t csr2csc_workspace_bytes(int M, int ncols, int64_t nnz);
 // colptr[ncols+1], row[nnz], val_t[nnz] (optional), perm[nnz] (optional): stable transpose

@@ -19,6 +19,10 @@ template <int RED, bool ARG> static SpmmLaunchFn by_comp(int comp) {
   case C_COPY: return &launch_spmm_rowseg<INST_VEC, INST_G, RED, C_COPY, ARG>;
   default: break;
   }
+  if (comp == C_MASK) {  // max/min backward wrt dense: SUM only, no arg output
+    if (RED == R_SUM && !ARG) return &launch_spmm_rowseg<INST_VEC, INST_G, R_SUM, C_MASK, false>;
+    return nullptr;
+  }
   if (ARG) return nullptr;  // arg index only exists on the torch face (multiply / no value)
   switch (comp) {
   case C_ADD: return &launch_spmm_rowseg<INST_VEC, INST_G, RED, C_ADD, false>;

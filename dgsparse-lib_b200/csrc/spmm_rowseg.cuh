@@ -44,6 +44,8 @@ struct SpmmArgs {
   int *tail_row;      // [num_chunks] row whose tail partial lives in slot 1, or -1
   int n_dst;          // 1 (local C) or the number of column-shard peers
   float *dst[kMaxDst];
+  const int *mask;    // COMP == C_MASK only: arg index tensor E of the forward, [*, ldm]
+  int64_t ldm;
 };
 
 constexpr int kSpmmThreads = 256;
@@ -70,6 +72,8 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
   constexpr int GPB = kSpmmThreads / G;  // groups (segments) per block
   constexpr int PER = kBatch / G;        // staged entries per lane per batch
   constexpr bool HAS_VAL = (COMP != C_COPY);
+  constexpr bool MASKED = (COMP == C_MASK);
+  constexpr int MV = MASKED ? VEC : 1;
   static_assert(kBatch % G == 0 && kBatch % U == 0, "bad tiling");
 
   // +1 pad: groups of one warp read the same slot index of different rows -> distinct banks
@@ -147,18 +151,21 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
       const int idx = base + gl + k * G;
       const bool ok = idx < hi;
       creg[k] = ok ? __ldcs(a.col + idx) : 0;   // col 0 keeps the speculative B load in bounds
-      if (HAS_VAL) vreg[k] = ok ? __ldcs(a.val + idx) : 0.0f;
+      if (HAS_VAL) vreg[k] = (MASKED && a.val == nullptr) ? 1.0f : (ok ? __ldcs(a.val + idx) : 0.0f);
     }
   };
   prefetch(lo);
 
   // one nnz: close the previous row if pos crossed its end, then fold compute(val, B-row) into acc
-  auto fold = [&](int pos, int j, int c, const float (&bv)[VEC]) {
+  auto fold = [&](int pos, int j, int c, const float (&bv)[VEC], const int (&mv)[MV]) {
     if (pos >= row_end) { finish_row(); advance_to(pos); }
     float x[VEC];
     const float ev = HAS_VAL ? s_val[grp][j] : 1.0f;
 #pragma unroll
-    for (int v = 0; v < VEC; v++) x[v] = compute_op<COMP>(ev, bv[v]);
+    for (int v = 0; v < VEC; v++) {
+      x[v] = compute_op<COMP>(ev, bv[v]);
+      if (MASKED) x[v] = (mv[v] == r) ? x[v] : 0.0f;   // include/cuda/spmm_cuda.cuh:400-433 (intended semantics)
+    }
     reduce_step<RED, ARG, VEC>(acc, arg, x, c);
   };
 
@@ -175,29 +182,40 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
 #pragma unroll 1
       for (int j0 = 0; j0 < kBatch; j0 += U) {
         float b[U][VEC];
+        int mk[U][MV];
         int cc[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
           cc[u] = s_col[grp][j0 + u];
-          if (active) ld_vec<VEC>(b[u], Bp + (size_t)cc[u] * a.ldb);
-          else {
+          if (active) {
+            ld_vec<VEC>(b[u], Bp + (size_t)cc[u] * a.ldb);
+            if (MASKED) ld_ivec<MV>(mk[u], a.mask + (size_t)cc[u] * a.ldm + colbase);
+          } else {
 #pragma unroll
             for (int v = 0; v < VEC; v++) b[u][v] = 0.0f;
+#pragma unroll
+            for (int v = 0; v < MV; v++) mk[u][v] = -1;
           }
         }
 #pragma unroll
-        for (int u = 0; u < U; u++) fold(base + j0 + u, j0 + u, cc[u], b[u]);
+        for (int u = 0; u < U; u++) fold(base + j0 + u, j0 + u, cc[u], b[u], mk[u]);
       }
     } else {
       // ragged last batch of the last segment
 #pragma unroll 1
       for (int j = 0; j < hi - base; j++) {
         float b[VEC];
+        int mk[MV];
         const int c = s_col[grp][j];
 #pragma unroll
         for (int v = 0; v < VEC; v++) b[v] = 0.0f;
-        if (active) ld_vec<VEC>(b, Bp + (size_t)c * a.ldb);
-        fold(base + j, j, c, b);
+#pragma unroll
+        for (int v = 0; v < MV; v++) mk[v] = -1;
+        if (active) {
+          ld_vec<VEC>(b, Bp + (size_t)c * a.ldb);
+          if (MASKED) ld_ivec<MV>(mk, a.mask + (size_t)c * a.ldm + colbase);
+        }
+        fold(base + j, j, c, b, mk);
       }
     }
     __syncwarp(gmask);

@@ -1,0 +1,125 @@
+"""Column-sharded SpMM across the GPUs of one box (BASELINE config 5).
+
+The feature axis shards naturally: every output column depends on one column of B only, for every
+reduce op.  The CSR is replicated; rank r owns columns [r*n_local, (r+1)*n_local) of B and of C.  The
+output panel is then made available on every rank, in one of two ways:
+
+  mode="peer"  (default when the ranks can map each other's memory): ONE kernel does both — the SpMM
+               epilogue stores each finished n_local-wide row segment straight into every rank's
+               row-major C[M, n_total] at column offset r*n_local through NVLink-mapped peer pointers
+               (CUDA IPC), so the transfer overlaps the remaining row segments; one stream-ordered
+               NCCL all-reduce of a single int afterwards is the completion barrier.
+  mode="nccl"  the baseline: local SpMM, then one ncclAllGather of the [M, n_local] panel into a
+               panel-major [world, M, n_local] buffer (panels_to_row_major() permutes when needed).
+
+No reduction is involved, so results are bit-identical to the single-GPU kernel.
+One process per GPU (torchrun); torch.distributed is used for the rendezvous, the handle exchange
+and the barrier only.
+"""
+import ctypes
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_columns(n_total: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, equal column panels; n_total must divide evenly (panels stay vector-aligned)."""
+    if world < 1 or n_total % world != 0:
+        raise ValueError(f"feature width {n_total} does not split evenly over {world} ranks")
+    n = n_total // world
+    return [(r * n, (r + 1) * n) for r in range(world)]
+
+
+def panels_to_row_major(panels: torch.Tensor) -> torch.Tensor:
+    """[world, M, n_local] (what an allgather of row panels yields) -> row-major [M, world*n_local]."""
+    w, m, n = panels.shape
+    return panels.permute(1, 0, 2).reshape(m, w * n)
+
+
+def exchange_objects(obj, group=None) -> list:
+    world = dist.get_world_size(group)
+    out = [None] * world
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
+class ColumnShardedSpMM:
+    def __init__(self, rowptr, col, values, n_local: int, reduce: int = 0, compute: int = 2, group=None,
+                 mode: Optional[str] = None):
+        from . import _lib
+        self._lib = _lib
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rowptr, self.col, self.values = rowptr, col, values
+        self.M, self.nnz = rowptr.numel() - 1, col.numel()
+        self.n_local, self.n_total = n_local, n_local * self.world
+        self.lo, self.hi = shard_columns(self.n_total, self.world)[self.rank]
+        self.reduce, self.compute = reduce, compute
+        dev = col.device
+        self.ws = torch.empty(max(256, _lib.lib.dgs_spmm_workspace_bytes(n_local, self.nnz, 0)), dtype=torch.uint8, device=dev)
+        self.C = torch.empty((self.M, self.n_total), dtype=torch.float32, device=dev)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._opened = []
+        self.mode = mode or ("peer" if self.world > 1 else "local")
+        if self.world > 1 and self.mode == "peer":
+            try:
+                self._map_peers()
+            except Exception as e:  # no IPC on this box: every rank must agree on the fallback
+                self._peer_error = str(e)
+                self.mode = "nccl"
+            agreed = exchange_objects(self.mode, group)
+            if any(m != "peer" for m in agreed):
+                self.mode = "nccl"
+        if self.mode == "nccl":
+            self.C_local = torch.empty((self.M, n_local), dtype=torch.float32, device=dev)
+            self.panels = torch.empty((self.world, self.M, n_local), dtype=torch.float32, device=dev)
+
+    def _map_peers(self):
+        L = self._lib
+        handle = ctypes.create_string_buffer(64)
+        off = ctypes.c_int64(0)
+        L.check(L.lib.dgs_ipc_export(self.C.data_ptr(), handle, ctypes.byref(off)), "dgs_ipc_export")
+        infos = exchange_objects((bytes(handle.raw), int(off.value)), self.group)
+        ptrs = []
+        for r, (h, o) in enumerate(infos):
+            if r == self.rank:
+                base = self.C.data_ptr()
+            else:
+                p = ctypes.c_void_p()
+                L.check(L.lib.dgs_ipc_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)), "dgs_ipc_open")
+                self._opened.append(p.value)
+                base = p.value + o
+            ptrs.append(base + self.lo * 4)          # every destination gets THIS rank's column panel
+        # dst[0] must be the local C
+        ptrs = [ptrs[self.rank]] + [p for r, p in enumerate(ptrs) if r != self.rank]
+        self._dst = (ctypes.c_void_p * len(ptrs))(*ptrs)
+
+    def __call__(self, B_local: torch.Tensor) -> torch.Tensor:
+        """B_local: [K, n_local] fp32 (this rank's column panel).  Returns row-major C[M, n_total] (peer /
+        local mode) or the panel-major [world, M, n_local] gather (nccl mode)."""
+        L = self._lib
+        lib, ptr = L.lib, L.ptr
+        stream = torch.cuda.current_stream(B_local.device).cuda_stream
+        if self.mode == "nccl":
+            L.check(lib.dgs_spmm_csr(self.M, self.n_local, self.nnz, ptr(self.rowptr), ptr(self.col), ptr(self.values),
+                                     ptr(B_local), B_local.stride(0), ptr(self.C_local), self.n_local, None, 0,
+                                     self.reduce, self.compute, ptr(self.ws), self.ws.numel(), stream), "dgs_spmm_csr")
+            dist.all_gather_into_tensor(self.panels, self.C_local, group=self.group)
+            return self.panels
+        if self.mode == "local":
+            dst = (ctypes.c_void_p * 1)(self.C.data_ptr())
+        else:
+            dst = self._dst
+        L.check(lib.dgs_spmm_csr_multi(self.M, self.n_local, self.nnz, ptr(self.rowptr), ptr(self.col), ptr(self.values),
+                                       ptr(B_local), B_local.stride(0), len(dst), dst, self.n_total, self.reduce,
+                                       self.compute, ptr(self.ws), self.ws.numel(), stream), "dgs_spmm_csr_multi")
+        if self.world > 1:
+            dist.all_reduce(self._flag, group=self.group)   # completion barrier: all peers' stores have landed
+        return self.C
+
+    def close(self):
+        for p in self._opened:
+            self._lib.lib.dgs_ipc_close(p)
+        self._opened = []

@@ -1,0 +1,98 @@
+/*
+ * dgsparse_b200.h — extended C ABI of libdgsparse_b200.so (stream-taking, error-returning).
+ *
+ * This is what the PyTorch face (dgsparse-lib_b200/dgsparse) binds through ctypes and what a C/C++
+ * caller should prefer over the legacy symbols of dgsparse.h.  Plain pointers and sizes only.
+ * Every function returns 0 on success or a cudaError_t value (dgs_last_error() gives the text).
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All data pointers are
+ * device pointers unless the function name ends in _host.
+ */
+#ifndef DGSPARSE_B200_H
+#define DGSPARSE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* REDUCEOP / COMPUTEOP of the reference, include/gspmm.h:13-14 (order is part of the gspmm-fp pybind
+ * surface, src/gspmm-fp/gspmm.cc:31-42). */
+enum dgsReduce { DGS_SUM = 0, DGS_MAX = 1, DGS_MIN = 2, DGS_MEAN = 3 };
+enum dgsCompute { DGS_ADD = 0, DGS_SUB = 1, DGS_MUL = 2, DGS_DIV = 3, DGS_COPY = 4, DGS_MASKMUL = 5 };
+
+int dgs_version(void);                 /* library version, major*10000 + minor*100 + patch */
+int dgs_cuda_version(void);            /* CUDA_VERSION the library was built with: src/version.cpp:11-21 */
+const char *dgs_last_error(void);      /* text of the last failure on this thread ("" if none) */
+int dgs_sm_count(void);
+
+/* Scratch the SpMM needs for rows cut by a segment boundary (see csrc/spmm_rowseg.cuh). */
+size_t dgs_spmm_workspace_bytes(int N, int64_t nnz, int with_arg);
+
+/* Generalized CSR SpMM:  C[r, :] = REDUCE_{p in row r} COMPUTE(val[p], B[col[p], :]).
+ * Replaces spmm_cuda(Tensor...) src/cuda/spmm_cuda.cu:14-253 (algorithm 0 semantics,
+ * include/cuda/spmm_cuda.cuh:10-55) and GSpMM_cuda / GSpMM_no_value_cuda src/gspmm-fp/gspmm.cu:442-473.
+ *   val NULL  -> no edge value (compute is ignored, COPY)
+ *   E non-NULL (MAX/MIN only) -> E[r, c] = column index of the winning nonzero, -1 for empty rows
+ *   empty row -> 0;  MEAN divides by the row's nnz count
+ *   n_dst > 1 -> the finished C rows are also stored to dst[1..] (NVLink peer pointers): the fused
+ *                column-shard epilogue.  dst[0] is the local C.  All share ldc. */
+int dgs_spmm_csr(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
+                 int64_t ldb, float *C, int64_t ldc, int *E, int64_t lde, int reduce, int compute, void *workspace,
+                 size_t workspace_bytes, void *stream);
+int dgs_spmm_csr_multi(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
+                       int64_t ldb, int n_dst, float *const *dst, int64_t ldc, int reduce, int compute, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* Masked SpMM of the max/min backward (grad wrt dense), called on the CSC arrays:
+ *   out[j, v] = sum_{p in ptr[j]..ptr[j+1]} [E[idx[p], v] == j] * val[p] * G[idx[p], v]
+ * Replaces spmm_cuda_with_mask src/cuda/spmm_cuda.cu:255-303 (intended semantics of
+ * include/cuda/spmm_cuda.cuh:400-433). */
+int dgs_spmm_csr_mask(int M, int N, int64_t nnz, const int *ptr, const int *idx, const float *val, const float *G,
+                      int64_t ldg, const int *E, int64_t lde, float *out, int64_t ldo, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+/* SDDMM: out[e] = dot(D1[row(e), :K], D2[col(e), :K]).  mean != 0 divides by the row degree
+ * (sddmmCSR{1,2}Scale<MEAN> include/cuda/sddmm_cuda.cuh:222-401); E non-NULL restricts the dot to the
+ * feature positions with E[row(e), c] == col(e) (sddmmCSR1Scale_with_mask :403-507).
+ * Replaces sddmm_cuda_csr / sddmm_cuda_coo src/cuda/spmm_cuda.cu:305-382 and src/sddmm/sddmm.cu:8-41. */
+int dgs_sddmm_csr(int M, int K, int64_t nnz, const int *rowptr, const int *col, const float *D1, int64_t ld1,
+                  const float *D2, int64_t ld2, const int *E, int mean, float *out, void *stream);
+int dgs_sddmm_coo(int K, int64_t nnz, const int *row, const int *col, const float *D1, int64_t ld1, const float *D2,
+                  int64_t ld2, float *out, void *stream);
+
+/* Exact stable CSR -> CSC.  Replaces csr2csc_cuda src/cuda/spmm_cuda.cu:384-414 (cuSPARSE) and the
+ * float permutation of dgsparse/storage.py:159-174.  val/val_t/row/perm may be NULL. */
+size_t dgs_csr2csc_workspace_bytes(int M, int ncols, int64_t nnz);
+int dgs_csr2csc(int M, int ncols, int64_t nnz, const int *rowptr, const int *col, const float *val, int *colptr,
+                int *row, float *val_t, int *perm, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Per row and head: softmax over the row's nonzeros of values[p*head + h] (see dgsparse.h). */
+int dgs_edge_softmax(int M, int head, const int *rowptr, const float *values, float *out, void *stream);
+
+/* Peer memory for the fused column-shard epilogue: export a device allocation to the other ranks of
+ * the box (CUDA IPC), open theirs; the opened base + offset is passed in dst[] of dgs_spmm_csr_multi. */
+int dgs_ipc_export(const void *dptr, void *handle64, int64_t *offset);
+int dgs_ipc_open(const void *handle64, void **base);
+int dgs_ipc_close(void *base);
+
+/* Per-launch device timing (bench.py's roofline leg): when enabled every kernel this library launches
+ * is bracketed by CUDA events on its stream.  dgs_profile_collect synchronises those events and returns
+ * the number of records written: kernel_ids[i] (1 = SpMM row-segment, 2 = SpMM fix-up, 3 = SDDMM,
+ * 4 = csr2csc passes, 5 = spconv) and ms[i]; it then clears the list. */
+int dgs_profile_enable(int on);
+int dgs_profile_collect(int max_records, int *kernel_ids, float *ms);
+
+/* HOST-buffer entry point (what a CPU-side caller of the reference's host functions would switch
+ * to): copies the CSR and B to the device, runs dgs_spmm_csr, copies C (and E) back, synchronises.
+ * All pointers are host pointers; pinned memory makes the copies asynchronous.  Device staging is
+ * cached per thread between calls. */
+int dgs_spmm_csr_host(int M, int K, int N, int64_t nnz, const int *rowptr, const int *col, const float *val,
+                      const float *B, float *C, int *E, int reduce, int compute);
+int dgs_sddmm_csr_host(int M, int Kdim, int ncols, int64_t nnz, const int *rowptr, const int *col, const float *D1,
+                       const float *D2, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGSPARSE_B200_H */

@@ -1,0 +1,48 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the column-sharded path (panel arithmetic, the
+object exchange used for IPC handles, panel-major -> row-major layout).  The kernels themselves need
+a GPU (tests -m gpu / bench.py --gpus N)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, os.path.join(ROOT, "dgsparse-lib_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dgsparse.distributed import shard_columns, panels_to_row_major, exchange_objects
+    n_total, M = 8, 5
+    lo, hi = shard_columns(n_total, world)[rank]
+    full = torch.arange(M * n_total, dtype=torch.float32).reshape(M, n_total)
+    mine = full[:, lo:hi].contiguous()                     # what this rank's SpMM would produce
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    ok = torch.equal(panels_to_row_major(torch.stack(gathered)), full)
+    infos = exchange_objects((bytes([rank]) * 64, rank * 256))
+    ok = ok and [o for _, o in infos] == [r * 256 for r in range(world)] and all(len(h) == 64 for h, _ in infos)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_column_shard_host_logic_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29000 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
+
+
+def test_shard_columns_rejects_ragged_split():
+    sys.path.insert(0, os.path.join(ROOT, "dgsparse-lib_b200"))
+    from dgsparse.distributed import shard_columns
+    assert shard_columns(512, 8) == [(64 * r, 64 * (r + 1)) for r in range(8)]
+    with pytest.raises(ValueError):
+        shard_columns(100, 8)

@@ -1,0 +1,210 @@
+"""GPU parity: CUDA SpMM / generalized SpMM (through the C ABI) vs the CPU oracle."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import assert_close_f32
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RED = {"sum": 0, "max": 1, "min": 2, "mean": 3}
+COMP = {"add": 0, "sub": 1, "mul": 2, "div": 3}
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def K():
+    import dgsparse._kernels as k
+    return k
+
+
+@pytest.mark.parametrize("name", ["p2p-Gnutella31", "ca-CondMat"])
+def test_config1_golden_feat32(K, oracle, graphs, name):
+    """BASELINE config 1: example/data CSR, feat=32, against the reference host function's own output."""
+    rowptr, col, (M, Kc) = graphs.load_fixture(name)
+    g = np.load(os.path.join(GOLDEN, name + "_spmm32.npz"))
+    sv, sb = (int(x) for x in g["seeds"])
+    val = graphs.uniform(col.size, sv)
+    B = graphs.uniform(Kc * 32, sb).reshape(Kc, 32)
+    out = K.spmm(dev(rowptr), dev(col), dev(val), dev(B)).cpu().numpy()
+    assert_close_f32(out[g["rows"]], g["out_rows"], what=f"{name} golden rows")
+    assert np.allclose(out.astype(np.float64).sum(0), g["colsum"], rtol=1e-6)
+    # legacy symbol spmm_cuda(m, k, rowptr, colind, values, dense, out) on stream 0
+    import dgsparse._lib as L
+    d = [dev(rowptr), dev(col), dev(val), dev(B)]
+    o2 = torch.empty(M, 32, device="cuda")
+    torch.cuda.synchronize()
+    L.lib.spmm_cuda(M, 32, *[t.data_ptr() for t in d], o2.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(o2.cpu().numpy(), out)
+    o3 = torch.empty(M, 32, device="cuda")
+    L.lib.spmm_cuda_no_edge_value(M, 32, d[0].data_ptr(), d[1].data_ptr(), None, d[3].data_ptr(), o3.data_ptr())
+    torch.cuda.synchronize()
+    assert_close_f32(o3.cpu().numpy(), oracle.spmm(rowptr, col, None, B), what="no_edge_value")
+
+
+@pytest.mark.parametrize("N", [1, 3, 4, 17, 32, 33, 64, 100, 128, 200, 256, 512])
+@pytest.mark.parametrize("reduce", ["sum", "max", "min", "mean"])
+def test_widths_and_reduces(K, oracle, graphs, N, reduce):
+    M, Kc = 3000, 2500
+    rowptr, col = graphs.random_csr(M, Kc, 90000, 100 + N, empty_frac=0.25, hub=2)
+    val = graphs.uniform(col.size, 1, 0.5, 1.5)
+    B = graphs.uniform(Kc * N, 2, -1.0, 1.0).reshape(Kc, N)
+    with_arg = reduce in ("max", "min")
+    got = K.spmm(dev(rowptr), dev(col), dev(val), dev(B), RED[reduce], COMP["mul"], with_arg=with_arg)
+    if with_arg:
+        ref, Eref = oracle.spmm(rowptr, col, val, B, reduce, "mul", with_arg=True)
+        out, E = got[0].cpu().numpy(), got[1].cpu().numpy()
+        assert np.array_equal(out, ref)         # max / min are exact
+        assert np.array_equal(E, Eref)          # first extremum wins, -1 on empty rows
+    else:
+        ref = oracle.spmm(rowptr, col, val, B, reduce, "mul")
+        ref64 = oracle.spmm_f64(rowptr, col, val, B, reduce, "mul")
+        assert_close_f32(got.cpu().numpy(), ref, ref64, what=f"N={N} {reduce}")
+
+
+@pytest.mark.parametrize("compute", ["add", "sub", "mul", "div"])
+@pytest.mark.parametrize("reduce", ["sum", "max", "min", "mean"])
+def test_gspmm_all_ops(oracle, graphs, compute, reduce):
+    """gspmm-fp surface: u_<op>_e_<reduce> and copy_u_<reduce> (example/gspmm-fp/util.py:17-110)."""
+    import dgsparse.gspmm as G
+    rowptr, col, (M, Kc) = graphs.load_fixture("p2p-Gnutella31")
+    N = 64
+    val = graphs.uniform(col.size, 3, 0.5, 1.5)
+    B = graphs.uniform(Kc * N, 4, -1.0, 1.0).reshape(Kc, N)
+    fn = getattr(G, f"u_{compute}_e_{reduce}")
+    out = fn(dev(rowptr), dev(col), dev(val).reshape(-1, 1), dev(B)).cpu().numpy()
+    ref = oracle.spmm(rowptr, col, val, B, reduce, compute)
+    if reduce in ("max", "min"):
+        assert np.array_equal(out, ref)
+    else:
+        assert_close_f32(out, ref, oracle.spmm_f64(rowptr, col, val, B, reduce, compute), what=fn.__name__)
+    if compute == "add":
+        cp = getattr(G, f"copy_u_{reduce}")(dev(rowptr), dev(col), dev(B)).cpu().numpy()
+        refc = oracle.spmm(rowptr, col, None, B, reduce)
+        if reduce in ("max", "min"):
+            assert np.array_equal(cp, refc)
+        else:
+            assert_close_f32(cp, refc, oracle.spmm_f64(rowptr, col, None, B, reduce), what="copy_u")
+
+
+def test_edge_cases(K, oracle, graphs):
+    # all rows empty
+    rowptr = np.zeros(11, np.int32)
+    col = np.zeros(0, np.int32)
+    B = graphs.uniform(5 * 8, 1).reshape(5, 8)
+    out, E = K.spmm(dev(rowptr), dev(col), None, dev(B), RED["max"], with_arg=True)
+    assert (out.cpu().numpy() == 0).all() and (E.cpu().numpy() == -1).all()
+    # one giant row (split over many segments) + trailing empty rows, every reduce
+    Kc, N = 70000, 64
+    cols = np.sort(np.random.default_rng(0).choice(Kc, 60000, replace=False)).astype(np.int32)
+    rowptr = np.array([0, 0, 60000, 60000, 60000], np.int32)
+    val = graphs.uniform(cols.size, 2, 0.5, 1.5)
+    B = graphs.uniform(Kc * N, 3, -1, 1).reshape(Kc, N)
+    for reduce in ["sum", "mean", "max", "min"]:
+        wa = reduce in ("max", "min")
+        got = K.spmm(dev(rowptr), dev(cols), dev(val), dev(B), RED[reduce], COMP["mul"], with_arg=wa)
+        if wa:
+            ref, Eref = oracle.spmm(rowptr, cols, val, B, reduce, with_arg=True)
+            assert np.array_equal(got[0].cpu().numpy(), ref) and np.array_equal(got[1].cpu().numpy(), Eref)
+        else:
+            assert_close_f32(got.cpu().numpy(), oracle.spmm(rowptr, cols, val, B, reduce),
+                             oracle.spmm_f64(rowptr, cols, val, B, reduce), what="giant row " + reduce)
+    # ties: all-equal features -> arg must be the FIRST nonzero's column (strict compare, spmm_cuda.cuh:38-42)
+    Bc = np.ones((Kc, 8), np.float32)
+    out, E = K.spmm(dev(rowptr), dev(cols), None, dev(Bc), RED["max"], with_arg=True)
+    assert (E.cpu().numpy()[1] == cols[0]).all()
+    # strided dense operand (column panel of a wider matrix): ldb != N
+    wide = graphs.uniform(Kc * 96, 5).reshape(Kc, 96)
+    panel = dev(wide)[:, 32:64]
+    assert not panel.is_contiguous()
+    import dgsparse._lib as L
+    outp = torch.empty(4, 32, device="cuda")
+    ws = torch.empty(L.lib.dgs_spmm_workspace_bytes(32, cols.size, 0), dtype=torch.uint8, device="cuda")
+    rp, cc, vv = dev(rowptr), dev(cols), dev(val)
+    L.check(L.lib.dgs_spmm_csr(4, 32, cols.size, rp.data_ptr(), cc.data_ptr(), vv.data_ptr(), panel.data_ptr(), 96,
+                               outp.data_ptr(), 32, None, 0, 0, 2, ws.data_ptr(), ws.numel(), None), "strided")
+    torch.cuda.synchronize()
+    assert_close_f32(outp.cpu().numpy(), oracle.spmm(rowptr, cols, val, wide[:, 32:64]),
+                     oracle.spmm_f64(rowptr, cols, val, wide[:, 32:64]), what="strided panel")
+
+
+def test_gespmm_descr_api_and_colmajor(oracle, graphs):
+    """gespmmCsrSpMM(SpMatCsrDescr_t, B, N, C, transpose_BC, alg) — src/ge-spmm/gespmm.h:9-33."""
+    import dgsparse._lib as L
+    M, Kc, N = 500, 400, 48
+    rowptr, col = graphs.random_csr(M, Kc, 6000, 5, empty_frac=0.1)
+    val = graphs.uniform(col.size, 1)
+    B = graphs.uniform(Kc * N, 2).reshape(Kc, N)
+    ref = oracle.spmm(rowptr, col, val, B)
+    rp, cc, vv = dev(rowptr), dev(col), dev(val)
+    d = L.SpMatCsrDescr_t(M, Kc, col.size, rp.data_ptr(), cc.data_ptr(), vv.data_ptr())
+    for alg in (0, 8, 10):
+        C = torch.empty(M, N, device="cuda")
+        L.lib.gespmmCsrSpMM(d, dev(B).data_ptr(), N, C.data_ptr(), True, alg)
+        torch.cuda.synchronize()
+        assert_close_f32(C.cpu().numpy(), ref, what=f"alg {alg}")
+    Bt = dev(np.ascontiguousarray(B.T))          # column-major B = row-major B^T
+    Ct = torch.empty(N, M, device="cuda")
+    L.lib.gespmmCsrSpMM(d, Bt.data_ptr(), N, Ct.data_ptr(), False, 4)
+    torch.cuda.synchronize()
+    assert_close_f32(Ct.cpu().numpy().T, ref, what="column-major")
+
+
+def test_host_buffer_entry(oracle, graphs):
+    """dgs_spmm_csr_host: the HOST-pointer entry bench.py's e2e leg times."""
+    import dgsparse._lib as L
+    M, Kc, N = 4000, 3000, 64
+    rowptr, col = graphs.random_csr(M, Kc, 150000, 9, empty_frac=0.2, hub=1)
+    val = graphs.uniform(col.size, 1)
+    B = graphs.uniform(Kc * N, 2).reshape(Kc, N)
+    C = np.empty((M, N), np.float32)
+    E = np.empty((M, N), np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.check(L.lib.dgs_spmm_csr_host(M, Kc, N, col.size, p(rowptr), p(col), p(val), p(B), p(C), None, 0, 2), "host sum")
+    assert_close_f32(C, oracle.spmm(rowptr, col, val, B), oracle.spmm_f64(rowptr, col, val, B), what="host sum")
+    L.check(L.lib.dgs_spmm_csr_host(M, Kc, N, col.size, p(rowptr), p(col), p(val), p(B), p(C), p(E), 1, 2), "host max")
+    ref, Eref = oracle.spmm(rowptr, col, val, B, "max", with_arg=True)
+    assert np.array_equal(C, ref) and np.array_equal(E, Eref)
+
+
+def test_reddit_like_scaled_parity(K, oracle, graphs):
+    """Same generator as the bench workload (config 2) at 1/16 scale: hub rows of thousands of nnz."""
+    rowptr, col = graphs.reddit_like(1 / 16)
+    M = rowptr.size - 1
+    val = graphs.uniform(col.size, 1)
+    B = graphs.uniform(M * 64, 2).reshape(M, 64)
+    out = K.spmm(dev(rowptr), dev(col), dev(val), dev(B)).cpu().numpy()
+    assert_close_f32(out, oracle.spmm(rowptr, col, val, B), oracle.spmm_f64(rowptr, col, val, B), what="reddit/16")
+
+
+def test_full_size_properties(K, graphs):
+    """BASELINE config 2 at full size (232 965 rows, 114.6 M nnz, feat 64): size-independent checks.
+    (1) column-sum identity  1^T (A B) = (A^T 1)^T B  in fp64;  (2) linearity in B;  (3) a sampled set
+    of rows recomputed with torch in fp64;  (4) determinism: two runs give identical bytes."""
+    rowptr, col = graphs.reddit_like(1.0)
+    M, nnz = rowptr.size - 1, col.size
+    rp, cc = dev(rowptr), dev(col)
+    val = torch.rand(nnz, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    B = torch.rand(M, 64, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    C = K.spmm(rp, cc, val, B)
+    w = torch.zeros(M, dtype=torch.float64, device="cuda").index_add_(0, cc.long(), val.double())
+    lhs = C.double().sum(0)
+    rhs = (w[:, None] * B.double()).sum(0)
+    assert torch.allclose(lhs, rhs, rtol=1e-6), (lhs - rhs).abs().max()
+    B2 = torch.rand(M, 64, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    C2 = K.spmm(rp, cc, val, B2)
+    C12 = K.spmm(rp, cc, val, B + 2 * B2)
+    assert torch.allclose(C12, C + 2 * C2, rtol=1e-5, atol=1e-3)
+    rows = np.unique(np.concatenate([np.arange(0, M, 2111), np.argsort(np.diff(rowptr))[-8:]]))
+    for r in rows:
+        s, e = int(rowptr[r]), int(rowptr[r + 1])
+        ref = (val[s:e].double()[:, None] * B[cc[s:e].long()].double()).sum(0)
+        assert torch.allclose(C[r].double(), ref, rtol=1e-5, atol=1e-6), r
+    assert torch.equal(C, K.spmm(rp, cc, val, B))
