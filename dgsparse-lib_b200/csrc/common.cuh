@@ -44,6 +44,13 @@ __device__ __forceinline__ int row_of_nnz(const int *__restrict__ rowptr, int M,
   return upper_bound_i32(rowptr, M + 1, p) - 1;
 }
 
+// base + row * stride_bytes as ONE mad.wide.u32 (row strides are < 4 GiB; the product may exceed 32 bits)
+__device__ __forceinline__ const char *row_addr(const char *base, unsigned row, unsigned stride_bytes) {
+  unsigned long long out;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(out) : "r"(row), "r"(stride_bytes), "l"((unsigned long long)base));
+  return reinterpret_cast<const char *>(out);
+}
+
 template <int VEC> struct VecT;
 template <> struct VecT<1> { using f = float;  using i = int;  };
 template <> struct VecT<2> { using f = float2; using i = int2; };

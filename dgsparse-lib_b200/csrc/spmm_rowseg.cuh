@@ -67,6 +67,11 @@ __device__ __forceinline__ void reduce_step(float (&acc)[VEC], int (&arg)[VEC], 
   }
 }
 
+// Shared-memory staging slot: (col, val bits) of one nonzero, read back with one LDS.64 broadcast.
+// Row stride 34 entries (272 B): rows of the groups of one warp start 4 banks apart -> conflict-free
+// 64-bit broadcasts, and every row stays 16-byte aligned.
+constexpr int kStageStride = kBatch + 2;
+
 template <int VEC, int G, int RED, int COMP, bool ARG, int U>
 __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArgs a) {
   constexpr int GPB = kSpmmThreads / G;  // groups (segments) per block
@@ -76,9 +81,8 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
   constexpr int MV = MASKED ? VEC : 1;
   static_assert(kBatch % G == 0 && kBatch % U == 0, "bad tiling");
 
-  // +1 pad: groups of one warp read the same slot index of different rows -> distinct banks
-  __shared__ int s_col[GPB][kBatch + 1];
-  __shared__ float s_val[HAS_VAL ? GPB : 1][kBatch + 1];
+  __shared__ __align__(16) int2 s_cv[HAS_VAL ? GPB : 1][kStageStride];
+  __shared__ __align__(16) int s_c[HAS_VAL ? 1 : GPB][kStageStride];
 
   const int grp = threadIdx.x / G;
   const int gl = threadIdx.x % G;
@@ -90,7 +94,12 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
   const int hi = (a.nnz - lo <= a.chunk) ? a.nnz : lo + a.chunk;
   const int colbase = blockIdx.y * (G * VEC) + gl * VEC;
   const bool active = colbase < a.N;
-  const float *__restrict__ Bp = a.B + colbase;
+  // lanes beyond a ragged N recompute panel 0 (always in bounds) and never store: no predication in the hot loop
+  const int ldcol = active ? colbase : 0;
+  const char *__restrict__ Bp = reinterpret_cast<const char *>(a.B + ldcol);
+  const char *__restrict__ Mp = MASKED ? reinterpret_cast<const char *>(a.mask + ldcol) : nullptr;
+  const unsigned ldb_bytes = (unsigned)(a.ldb * 4);   // one IMAD.WIDE.U32 per gather address
+  const unsigned ldm_bytes = MASKED ? (unsigned)(a.ldm * 4) : 0u;
   const int *__restrict__ rowptr = a.rowptr;
 
   int r = row_of_nnz(rowptr, a.M, lo);
@@ -122,7 +131,8 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
 #pragma unroll
         for (int v = 0; v < VEC; v++) o[v] = a.mean ? acc[v] / deg : acc[v];
         const size_t off = (size_t)r * a.ldc + colbase;
-        for (int d = 0; d < a.n_dst; d++) st_vec_cs<VEC>(a.dst[d] + off, o);
+        st_vec_cs<VEC>(a.dst[0] + off, o);
+        for (int d = 1; d < a.n_dst; d++) st_vec_cs<VEC>(a.dst[d] + off, o);   // NVLink peers
         if (ARG) st_vec_cs<VEC>(a.E + (size_t)r * a.lde + colbase, arg);
       } else {
         store_partial(0);     // the row began in an earlier segment: head partial
@@ -156,11 +166,9 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
   };
   prefetch(lo);
 
-  // one nnz: close the previous row if pos crossed its end, then fold compute(val, B-row) into acc
-  auto fold = [&](int pos, int j, int c, const float (&bv)[VEC], const int (&mv)[MV]) {
-    if (pos >= row_end) { finish_row(); advance_to(pos); }
+  // acc (+)= compute(val, B-row) for one nonzero
+  auto accumulate = [&](int c, float ev, const float (&bv)[VEC], const int (&mv)[MV]) {
     float x[VEC];
-    const float ev = HAS_VAL ? s_val[grp][j] : 1.0f;
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
       x[v] = compute_op<COMP>(ev, bv[v]);
@@ -169,36 +177,45 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
     reduce_step<RED, ARG, VEC>(acc, arg, x, c);
   };
 
+  auto gather = [&](int c, float (&bv)[VEC], int (&mv)[MV]) {
+    ld_vec<VEC>(bv, reinterpret_cast<const float *>(row_addr(Bp, (unsigned)c, ldb_bytes)));
+    if (MASKED) ld_ivec<MV>(mv, reinterpret_cast<const int *>(row_addr(Mp, (unsigned)c, ldm_bytes)));
+  };
+
   for (int base = lo; base < hi; base += kBatch) {
 #pragma unroll
     for (int k = 0; k < PER; k++) {
-      s_col[grp][gl + k * G] = creg[k];
-      if (HAS_VAL) s_val[grp][gl + k * G] = vreg[k];
+      if (HAS_VAL) s_cv[grp][gl + k * G] = make_int2(creg[k], __float_as_int(vreg[k]));
+      else s_c[grp][gl + k * G] = creg[k];
     }
     __syncwarp(gmask);
     prefetch(base + kBatch);
     if (hi - base >= kBatch) {
-      // full batch: U row gathers in flight before the first one is consumed
 #pragma unroll 1
       for (int j0 = 0; j0 < kBatch; j0 += U) {
+        // U row gathers in flight before the first one is consumed
         float b[U][VEC];
         int mk[U][MV];
         int cc[U];
+        float ev[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          cc[u] = s_col[grp][j0 + u];
-          if (active) {
-            ld_vec<VEC>(b[u], Bp + (size_t)cc[u] * a.ldb);
-            if (MASKED) ld_ivec<MV>(mk[u], a.mask + (size_t)cc[u] * a.ldm + colbase);
-          } else {
+          if (HAS_VAL) { const int2 t = s_cv[grp][j0 + u]; cc[u] = t.x; ev[u] = __int_as_float(t.y); }
+          else { cc[u] = s_c[grp][j0 + u]; ev[u] = 1.0f; }
+          gather(cc[u], b[u], mk[u]);
+        }
+        const int p0 = base + j0;
+        if (p0 + U <= row_end) {
+          // fast path: the U nonzeros all belong to the current row
 #pragma unroll
-            for (int v = 0; v < VEC; v++) b[u][v] = 0.0f;
+          for (int u = 0; u < U; u++) accumulate(cc[u], ev[u], b[u], mk[u]);
+        } else {
 #pragma unroll
-            for (int v = 0; v < MV; v++) mk[u][v] = -1;
+          for (int u = 0; u < U; u++) {
+            if (p0 + u >= row_end) { finish_row(); advance_to(p0 + u); }
+            accumulate(cc[u], ev[u], b[u], mk[u]);
           }
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) fold(base + j0 + u, j0 + u, cc[u], b[u], mk[u]);
       }
     } else {
       // ragged last batch of the last segment
@@ -206,16 +223,13 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
       for (int j = 0; j < hi - base; j++) {
         float b[VEC];
         int mk[MV];
-        const int c = s_col[grp][j];
-#pragma unroll
-        for (int v = 0; v < VEC; v++) b[v] = 0.0f;
-#pragma unroll
-        for (int v = 0; v < MV; v++) mk[v] = -1;
-        if (active) {
-          ld_vec<VEC>(b, Bp + (size_t)c * a.ldb);
-          if (MASKED) ld_ivec<MV>(mk, a.mask + (size_t)c * a.ldm + colbase);
-        }
-        fold(base + j, j, c, b, mk);
+        int c;
+        float ev = 1.0f;
+        if (HAS_VAL) { const int2 t = s_cv[grp][j]; c = t.x; ev = __int_as_float(t.y); }
+        else c = s_c[grp][j];
+        gather(c, b, mk);
+        if (base + j >= row_end) { finish_row(); advance_to(base + j); }
+        accumulate(c, ev, b, mk);
       }
     }
     __syncwarp(gmask);
