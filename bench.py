@@ -58,6 +58,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload):
+    """Per-launch DRAM traffic of the dominant kernel from the committed ncu capture (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))[workload]["traffic_bytes"]
+    except Exception:
+        return None
+
+
 def algorithmic_bytes_spmm(M, nnz, N, k_touched, has_value, with_arg=False):
     """rowptr + col + val + each referenced B row once + C (+ E for max/min)."""
     return 4 * (M + 1) + 4 * nnz + (4 * nnz if has_value else 0) + 4 * k_touched * N + 4 * M * N + (4 * M * N if with_arg else 0)
@@ -330,7 +339,8 @@ def main():
                        "l2": "no flush: inputs per step (%.0f MB) exceed the 126 MB L2" % (alg_bytes / 1e6)},
             "achieved_hbm_gbs": alg_bytes * (world) / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak,
+                         "traffic": ncu_traffic(args.workload) if args.scale == 1.0 else None, "peak_source": peak_src,
                          "kernel": "spmm_rowseg_kernel" if main_id == 1 else "sddmm_kernel",
                          "kernel_ms_avg": k_avg, "fixup_ms_avg": (sum(fix_ms) / len(fix_ms)) if fix_ms else None,
                          "algorithmic_bytes_per_launch": alg_bytes,

@@ -1,0 +1,56 @@
+"""Worker for tests/test_multigpu_gpu.py (launched under torchrun, one rank per GPU)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "dgsparse-lib_b200")):
+    sys.path.insert(0, p)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=dev)
+    import dgsparse._kernels as K
+    import dgsparse._lib as L
+    from dgsparse.distributed import ColumnShardedSpMM, panels_to_row_major
+    from tools import graphs
+    M, n_local = 20000, 64
+    rowptr, col = graphs.random_csr(M, M, 600000, 31, empty_frac=0.2, hub=2)
+    val = graphs.uniform(col.size, 1)
+    Bfull = graphs.uniform(M * n_local * world, 2, -1, 1).reshape(M, n_local * world)
+    rp, cc, vv = (torch.from_numpy(a).to(dev) for a in (rowptr, col, val))
+    Bf = torch.from_numpy(Bfull).to(dev)
+    ref = K.spmm(rp, cc, vv, Bf)                                   # single-GPU kernel on the full width
+    B_local = Bf[:, rank * n_local:(rank + 1) * n_local].contiguous()
+    for reduce in (L.SUM, L.MAX):
+        refr = K.spmm(rp, cc, vv, Bf, reduce, L.MUL)
+        for mode in ("peer", "nccl"):
+            op = ColumnShardedSpMM(rp, cc, vv, n_local, reduce=reduce, mode=mode)
+            for it in range(3):
+                out = op(B_local)
+            torch.cuda.synchronize()
+            C = out if op.mode == "peer" else panels_to_row_major(out)
+            ok = torch.equal(C, refr)                              # no reduction across ranks: bit-identical
+            flag = torch.tensor([int(ok)], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if rank == 0:
+                print(f"mode requested={mode} used={op.mode} reduce={reduce} identical={bool(flag.item())}", flush=True)
+            assert flag.item() == 1, (mode, reduce)
+            if mode == "peer" and rank == 0 and op.mode != "peer":
+                print("PEER MAPPING UNAVAILABLE:", getattr(op, "_peer_error", "?"), flush=True)
+            dist.barrier()
+            op.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU_OK", flush=True)
+
+
+if __name__ == "__main__":
+    main()
