@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--mode", default=None, choices=[None, "peer", "nccl"], help="N>1 exchange (default: peer)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
     return ap.parse_args()
 
 
@@ -181,6 +182,53 @@ def cpu_reference_run(wl, steps, warmup, budget_s=12.0):
                       f"full B [{M},{N}], {steps} timed passes, row blocks spread over {cores} host threads",
             "ms_per_sample": t * 1e3}
     return gflops, info
+
+
+def reference_cuda_run(wl, M, N, nnz, rp, cc, vv, B, D1, D2, our_step, steps, warmup, flop):
+    """Times the reference's CUDA C ABI (compiled unmodified for sm_100a into oracle/_ref/libref_cuda.so)
+    on the same device buffers, and compares its output with ours.  Test/bench infrastructure only."""
+    import torch
+    from oracle import oracle
+    R = oracle.ref_cuda_lib()
+    if R is None:
+        return {"unavailable": "oracle/_ref/libref_cuda.so was not built (reference tree absent at build time)"}
+    dev = rp.device
+    if wl["op"] == "sddmm_csr":
+        ref_out = torch.zeros(nnz, device=dev)
+        our_out = torch.empty(1, nnz, device=dev)
+        import dgsparse._lib as L
+
+        def ref_step():
+            R.sddmm_cuda_csr(M, N, nnz, rp.data_ptr(), cc.data_ptr(), D1.data_ptr(), D2.data_ptr(), ref_out.data_ptr())
+        L.check(L.lib.dgs_sddmm_csr(M, N, nnz, rp.data_ptr(), cc.data_ptr(), D1.data_ptr(), N, D2.data_ptr(), N,
+                                    None, 0, our_out.data_ptr(), torch.cuda.current_stream().cuda_stream), "sddmm")
+        what = "sddmm_cuda_csr (src/sddmm/sddmm.cu:25-41)"
+    elif wl["op"] == "spmm_sum":
+        ref_out = torch.zeros(M, N, device=dev)
+        import dgsparse._lib as L
+        import dgsparse._kernels as K
+        our_out = K.spmm(rp, cc, vv, B, L.SUM, L.MUL)
+
+        def ref_step():
+            R.spmm_cuda(M, N, rp.data_ptr(), cc.data_ptr(), vv.data_ptr(), B.data_ptr(), ref_out.data_ptr())
+        what = "spmm_cuda -> gespmmCsrSpMM (src/ge-spmm/gespmm.cc:29-123)"
+    else:
+        return {"unavailable": f"the reference's C ABI has no {wl['op']} (gspmm-fp is a torch pybind module)"}
+    for _ in range(warmup):
+        ref_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ref_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    a, b = our_out.reshape(-1), ref_out.reshape(-1)
+    err = float(((a - b).abs() / b.abs().clamp_min(1e-6)).max().item())
+    return {"kernel": what, "ms_per_step": ms, "value": flop / (ms * 1e-3) / 1e9, "unit": "GFLOP/s",
+            "max_rel_diff_ours_vs_reference_cuda": err,
+            "note": "device-resident, default stream, same buffers and step count as `value`"}
 
 
 def main():
@@ -325,6 +373,13 @@ def main():
                "d2h_bytes_per_step": 4 * M * N, "ms_per_step": float(te.item()) * 1e3, "steps": ksteps,
                "api": "dgs_spmm_csr_host (include/dgsparse_b200.h): pinned host CSR + B in, C out, every step"}
 
+    # --- the reference's own CUDA kernels (oracle/_ref/libref_cuda.so, built unmodified for sm_100a) on the
+    #     same device buffers, same timing loop: the "vs reference CUDA" comparison of SURVEY.md §8d.
+    ref_cuda = None
+    if world == 1 and not args.no_ref_cuda:
+        ref_cuda = reference_cuda_run(wl, M, N, nnz, rp, cc, vv, locals().get("B"), locals().get("D1"),
+                                      locals().get("D2"), step, args.steps, max(args.warmup, 3), flop)
+
     if rank == 0:
         k_avg = sum(kern_ms) / max(1, len(kern_ms)) if kern_ms else ms_per_step
         achieved = alg_bytes / (k_avg * 1e-3) / 1e9
@@ -352,6 +407,8 @@ def main():
         line.update(extra)
         if e2e is not None:
             line["e2e"] = e2e
+        if ref_cuda is not None:
+            line["reference_cuda"] = ref_cuda
         if world == 1 and not args.no_cpu_baseline and wl["op"] != "sddmm_csr":
             try:
                 _, info = cpu_reference_run(wl, steps=2, warmup=1, budget_s=12.0)

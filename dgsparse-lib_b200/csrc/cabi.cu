@@ -9,6 +9,7 @@
 #include "../../include/dgsparse_b200.h"
 #include "common.cuh"
 #include "spmm.h"
+#include "spconv.h"
 
 namespace {
 
@@ -172,6 +173,47 @@ int dgs_edge_softmax(int M, int head, const int *rowptr, const float *values, fl
   const int blocks = (int)(((int64_t)M * 32 + 255) / 256);
   edge_softmax_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(M, head, rowptr, values, out);
   return ok_or(cudaGetLastError(), "dgs_edge_softmax");
+}
+
+// ---- sparse convolution ---------------------------------------------------------------------------
+size_t dgs_spconv_workspace_bytes(int k_vol, int c_in, int c_out, int precision) {
+  return dgs::spconv_workspace_bytes(k_vol, c_in, c_out, precision);
+}
+
+int dgs_spconv_fwd(int in_nnz, int out_nnz, int k_vol, int c_in, int c_out, const int *kpos, const int *qkpos,
+                   const int *in_map, const int *out_map, int64_t sum_nnz, const float *in_feats, const float *kernel,
+                   float *out_feats, int separate_mid, int precision, void *workspace, size_t workspace_bytes,
+                   void *stream) {
+  if (separate_mid && in_nnz != out_nnz) return fail(cudaErrorInvalidValue, "dgs_spconv_fwd(separate_mid needs in_nnz == out_nnz)");
+  dgs::SpconvProblem p;
+  p.k_vol = k_vol; p.kdim = c_in; p.ndim = c_out; p.kpos = kpos; p.qkpos = qkpos; p.imap = in_map; p.omap = out_map;
+  p.sum_nnz = sum_nnz; p.in = in_feats; p.ld_in = c_in; p.in_rows = in_nnz;
+  p.W = kernel; p.w_sc = c_out; p.w_sn = 1; p.w_sk = (int64_t)c_in * c_out;
+  p.out = out_feats; p.ld_out = c_out; p.out_rows = out_nnz; p.precision = precision; p.separate_mid = separate_mid;
+  return ok_or(dgs::spconv_gemm(p, workspace, workspace_bytes, (cudaStream_t)stream), "dgs_spconv_fwd");
+}
+
+int dgs_spconv_bwd(int in_nnz, int out_nnz, int k_vol, int c_in, int c_out, const int *kpos, const int *qkpos,
+                   const int *in_map, const int *out_map, int64_t sum_nnz, const float *out_grad, const float *in_feats,
+                   const float *kernel, float *in_grad, float *kernel_grad, int separate_mid, int precision,
+                   void *workspace, size_t workspace_bytes, void *stream) {
+  if (separate_mid && in_nnz != out_nnz) return fail(cudaErrorInvalidValue, "dgs_spconv_bwd(separate_mid needs in_nnz == out_nnz)");
+  if (in_grad != nullptr) {   // the forward with the maps swapped and W[k] read transposed
+    dgs::SpconvProblem p;
+    p.k_vol = k_vol; p.kdim = c_out; p.ndim = c_in; p.kpos = kpos; p.qkpos = qkpos; p.imap = out_map; p.omap = in_map;
+    p.sum_nnz = sum_nnz; p.in = out_grad; p.ld_in = c_out; p.in_rows = out_nnz;
+    p.W = kernel; p.w_sc = 1; p.w_sn = c_out; p.w_sk = (int64_t)c_in * c_out;
+    p.out = in_grad; p.ld_out = c_in; p.out_rows = in_nnz; p.precision = precision; p.separate_mid = separate_mid;
+    int rc = ok_or(dgs::spconv_gemm(p, workspace, workspace_bytes, (cudaStream_t)stream), "dgs_spconv_bwd(in_grad)");
+    if (rc) return rc;
+  }
+  if (kernel_grad != nullptr) {
+    int rc = ok_or(dgs::spconv_wgrad(k_vol, c_in, c_out, kpos, qkpos, in_map, out_map, sum_nnz, in_feats, c_in, in_nnz,
+                                     out_grad, c_out, kernel_grad, precision, separate_mid, (cudaStream_t)stream),
+                   "dgs_spconv_bwd(kernel_grad)");
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 // ---- host-buffer entry points --------------------------------------------------------------------

@@ -1,0 +1,582 @@
+// spconv.cu — sparse 3-D convolution, fused gather-GEMM-scatter (forward and the dX backward), for sm_100a.
+//
+//   out[omap[p], :] += in[imap[p], :] @ W[k]      for every kernel offset k, pair p in [kpos[k], kpos[k+1])
+//
+// Replaces spconv_fwd_fused / spconv_bwd_fused (dX half) of the reference, src/cuda/spconv_cuda.cu:18-253, and its
+// _fgms_fusion_{fp32,tf32,fp16_tc4}* kernels, include/cuda/spconv.cuh (tf32 model kernel :1100-1248).
+//
+// B200 design (tensor path): the pair list of every kernel offset is cut into tiles of 128 pairs (the
+// reference's q = 128 quantisation of kpos -> qkpos, test/test_spconv.py:5-14, so one tile never mixes two
+// offsets).  A CTA of 4 warps takes a run of consecutive tiles.  Per tile it
+//   1. gathers the 128 input rows named by imap with 16-byte loads (8 lanes cover one 128-byte row segment),
+//      rounds them to tf32 (cvt.rna) or packs them to bf16, and writes them into shared memory in the UMMA
+//      canonical K-major SWIZZLE_128B layout (row r, 16-byte chunk c -> r*128 + ((c ^ (r & 7)) << 4));
+//   2. keeps W[k]^T (pre-transposed / pre-converted once per call by spconv_prep_weights_kernel, so that it is
+//      K-major too) resident in shared memory while consecutive tiles share the same offset k;
+//   3. one elected thread issues tcgen05.mma (kind::tf32 or kind::f16, M = 128, N = c_out tile, K = 8 or 16 per
+//      instruction) with the fp32 accumulator in TMEM, and commits to an mbarrier;
+//   4. every warp reads its 32 accumulator rows back with tcgen05.ld (thread t = pair t of the tile) and
+//      scatters them with vectorised red.global.add.v4.f32 into out[omap[p], :].
+// Several CTAs are resident per SM (48 KB smem, <= 128 TMEM columns each) so one CTA's gather overlaps another's
+// MMA and scatter.  The exact-fp32 path (arch80 = false in the reference) is a SIMT kernel further down.
+//
+// Fixes of the reference: the output is zeroed by the call, every dtype path writes fp32 into the fp32
+// output, `separate_mid` runs the centre offset as identity-mapped tiles of the same kernel instead of a cuBLAS call.
+#include <cuda_bf16.h>
+#include <cstdint>
+#include "common.cuh"
+#include "spmm.h"
+#include "spconv.h"
+
+namespace dgs {
+namespace {
+
+constexpr int kTileM = 128;          // pairs per tile == UMMA M == the reference's q
+constexpr int kAtomBytes = 128;      // one swizzle row: 32 tf32 or 64 bf16 channels
+constexpr int kMaxAtomsPerGroup = 2; // K staged per MMA group: 64 fp32 / 128 bf16 channels
+constexpr int kMaxNT = 128;          // widest c_out tile (TMEM columns)
+
+struct SpconvArgs {
+  const int *kpos, *qkpos, *imap, *omap;
+  const float *in;     // [in_rows, ld_in]
+  const uint8_t *Wt;   // [k_vol][n_rows_pad][k_pad] in the MMA dtype, K contiguous (prep kernel)
+  float *out;          // [out_rows, ld_out]
+  int64_t ld_in, ld_out;
+  int k_vol, c_in, c_out;     // GEMM K and N of this launch (swapped for the dX backward)
+  int n_atoms;                // K atoms: ceil(c_in / elements per atom)
+  int n_rows_pad;             // rows of Wt per offset (gridDim.y * NT)
+  int NT;                     // c_out tile, multiple of 16, <= 128
+  int tmem_cols;              // power of two >= max(32, NT)
+  int n_map_tiles;            // tiles driven by kpos/qkpos/imap/omap
+  int n_id_tiles;             // identity-mapped tiles of the centre offset (separate_mid)
+  int id_rows, mid_k;         // rows covered by the identity tiles, centre offset index
+  int tiles_per_cta;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  const uint32_t a = smem_u32(bar);
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address
+// >> 4 in [0,14), LBO >> 4 in [16,30) (unused for swizzled K-major), SBO >> 4 in [32,46) = 1024 B between 8-row
+// groups, version 1 in [46,48), layout type 2 (SWIZZLE_128B) in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (1 << 4), A/B format in [7,10)/[10,13)
+// (2 = tf32, 1 = bf16), both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
+template <int KIND> __device__ __forceinline__ uint32_t umma_idesc(int n) {
+  const uint32_t fmt = KIND == 0 ? 2u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+template <int KIND> __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND == 0)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 16 consecutive fp32 accumulator columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+
+template <int KIND> struct Kind;
+template <> struct Kind<0> { static constexpr int kElemBytes = 4, kElemsPerAtom = 32, kUmmaK = 8; };   // tf32
+template <> struct Kind<1> { static constexpr int kElemBytes = 2, kElemsPerAtom = 64, kUmmaK = 16; };  // bf16
+
+// One 16-byte shared-memory chunk of a gathered row: channels [ch, ch + 16 / elem bytes) of `row` (zeros when the
+// row is padding or the channels lie beyond c_in).
+template <int KIND> __device__ __forceinline__ uint4 gather_chunk(const float *in, int64_t ld_in, int row, int ch, int c_in) {
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (row < 0) return o;
+  const float *src = in + (int64_t)row * ld_in + ch;
+  if (KIND == 0) {
+    if (ch < c_in) {  // c_in % 4 == 0: a chunk is all-or-nothing
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(src));
+      o = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    }
+  } else {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (ch < c_in) a = __ldg(reinterpret_cast<const float4 *>(src));
+    if (ch + 4 < c_in) b = __ldg(reinterpret_cast<const float4 *>(src + 4));
+    o = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+  return o;
+}
+
+// ---- the fused tile kernel ------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(128) spconv_fgms_tc_kernel(const SpconvArgs a) {
+  using KD = Kind<KIND>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_inrow[kTileM];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // 1024-byte aligned operand buffers (SWIZZLE_128B atoms are 8 rows x 128 B)
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int ga_max = a.n_atoms < kMaxAtomsPerGroup ? a.n_atoms : kMaxAtomsPerGroup;
+  const uint32_t sA = base;                                       // [ga][128 rows][128 B]
+  const uint32_t sW = base + (uint32_t)ga_max * kTileM * kAtomBytes;  // [ga][NT rows][128 B]
+  const bool w_resident = a.n_atoms <= kMaxAtomsPerGroup;         // whole K fits one group: keep W[k] across tiles
+
+  if (warp == 0) tmem_alloc(&s_tmem, (uint32_t)a.tmem_cols);
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t idesc = umma_idesc<KIND>(a.NT);
+  const int n0 = blockIdx.y * a.NT;
+  uint32_t phase = 0;
+  int resident_k = -1;
+
+  const int n_tiles = a.n_map_tiles + a.n_id_tiles;
+  const int t_begin = blockIdx.x * a.tiles_per_cta;
+  const int t_end = min(n_tiles, t_begin + a.tiles_per_cta);
+
+  for (int tile = t_begin; tile < t_end; tile++) {
+    // ---- which pairs: offset k, this thread's (input row, output row) ----
+    int k, in_row = -1, out_row = -1;
+    if (tile < a.n_map_tiles) {
+      const int q0 = tile * kTileM;
+      k = upper_bound_i32(a.qkpos, a.k_vol + 1, q0) - 1;
+      const int p = q0 - __ldg(a.qkpos + k) + __ldg(a.kpos + k) + tid;
+      if (p < __ldg(a.kpos + k + 1)) { in_row = __ldg(a.imap + p); out_row = __ldg(a.omap + p); }
+    } else {
+      k = a.mid_k;
+      const int r = (tile - a.n_map_tiles) * kTileM + tid;
+      if (r < a.id_rows) in_row = out_row = r;
+    }
+    s_inrow[tid] = in_row;
+    __syncthreads();
+
+    for (int a0 = 0; a0 < a.n_atoms; a0 += kMaxAtomsPerGroup) {
+      const int ga = min(kMaxAtomsPerGroup, a.n_atoms - a0);
+      // ---- gather A: item = (row, atom, 16 B chunk); 8 consecutive lanes = one 128 B row segment ----
+      const int per_thread = ga * 8;  // 128 rows * ga * 8 chunks / 128 threads
+      for (int it0 = 0; it0 < per_thread; it0 += 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int idx = (it0 + u) * 128 + tid;
+          const int c = idx & 7, at = (idx >> 3) % ga, r = idx / (8 * ga);
+          const int ch = (a0 + at) * KD::kElemsPerAtom + c * (16 / KD::kElemBytes);
+          v[u] = gather_chunk<KIND>(a.in, a.ld_in, s_inrow[r], ch, a.c_in);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int idx = (it0 + u) * 128 + tid;
+          const int c = idx & 7, at = (idx >> 3) % ga, r = idx / (8 * ga);
+          const uint32_t dst = sA + (uint32_t)at * (kTileM * kAtomBytes) + (uint32_t)r * kAtomBytes + (uint32_t)((c ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[u].x), "r"(v[u].y), "r"(v[u].z), "r"(v[u].w) : "memory");
+        }
+      }
+      // ---- W[k]^T rows [n0, n0 + NT), atoms [a0, a0 + ga): straight copy of the prepared K-major panel ----
+      if (!(w_resident && resident_k == k)) {
+        const int k_pad_bytes = a.n_atoms * kAtomBytes;
+        const uint8_t *wk = a.Wt + ((size_t)k * a.n_rows_pad + n0) * k_pad_bytes + (size_t)a0 * kAtomBytes;
+        const int items = a.NT * ga * 8;
+        for (int idx = tid; idx < items; idx += 128) {
+          const int c = idx & 7, at = (idx >> 3) % ga, n = idx / (8 * ga);
+          const uint4 w = __ldg(reinterpret_cast<const uint4 *>(wk + (size_t)n * k_pad_bytes + at * kAtomBytes + c * 16));
+          const uint32_t dst = sW + (uint32_t)at * (a.NT * kAtomBytes) + (uint32_t)n * kAtomBytes + (uint32_t)((c ^ (n & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+        }
+        resident_k = k;
+      }
+      fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        for (int at = 0; at < ga; at++) {
+          const int ch0 = (a0 + at) * KD::kElemsPerAtom;
+          const int ksteps = (min(KD::kElemsPerAtom, a.c_in - ch0) + KD::kUmmaK - 1) / KD::kUmmaK;
+          for (int ks = 0; ks < ksteps; ks++) {
+            // advancing K inside the 128 B swizzle row = advancing the start address by 32 B per step
+            const uint64_t ad = umma_desc_k128(sA + (uint32_t)at * (kTileM * kAtomBytes) + (uint32_t)ks * 32);
+            const uint64_t bd = umma_desc_k128(sW + (uint32_t)at * (a.NT * kAtomBytes) + (uint32_t)ks * 32);
+            umma<KIND>(tmem, ad, bd, idesc, (a0 + at + ks) > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&s_bar);      // implies tcgen05.fence::before_thread_sync
+      }
+      mbar_wait(&s_bar, phase);   // MMAs of this group done: smem reusable, accumulator readable
+      phase ^= 1u;
+    }
+    tc_fence_after();
+
+    // ---- scatter: thread t owns accumulator row t (TMEM lane 32*warp + lane) ----
+    float *orow = out_row >= 0 ? a.out + (int64_t)out_row * a.ld_out : nullptr;
+    for (int c0 = 0; c0 < a.NT; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (orow != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const int col = n0 + c0 + j;
+          if (col + 3 < a.c_out) {
+            red_add_v4(orow + col, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+              if (col + e < a.c_out) atomicAdd(orow + col + e, v[j + e]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();              // accumulator drained and s_inrow consumed before the next tile overwrites them
+    tc_fence_after();
+  }
+
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
+}
+
+// ---- W preparation: Wt[k][n][c] = W[k][c * sc + n * sn] converted to the MMA dtype, zero padded -----------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) spconv_prep_weights_kernel(const float *__restrict__ W, uint8_t *__restrict__ Wt, int k_vol,
+                                                                  int kdim, int ndim, int k_pad, int n_rows_pad, int64_t sc,
+                                                                  int64_t sn, int64_t sk) {
+  const int64_t total = (int64_t)k_vol * n_rows_pad * k_pad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % k_pad);
+    const int n = (int)((i / k_pad) % n_rows_pad);
+    const int k = (int)(i / ((int64_t)k_pad * n_rows_pad));
+    float v = 0.0f;
+    if (c < kdim && n < ndim) v = __ldg(W + (int64_t)k * sk + (int64_t)c * sc + (int64_t)n * sn);
+    if (KIND == 0) reinterpret_cast<uint32_t *>(Wt)[i] = to_tf32(v);
+    else reinterpret_cast<__nv_bfloat16 *>(Wt)[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---- exact fp32 SIMT path (the reference's arch80 = false kernels, _fgms_fusion_fp32*) --------------------------------
+// One warp per group of 4 pairs of the same offset; lane l owns output channels l, l + 32, ... (<= 8 per lane, i.e.
+// c_out <= 256 per pass); W rows are read once per 4 pairs.  Products are accumulated ci-ascending like cpu_compute.
+constexpr int kSimtPairs = 4;
+constexpr int kSimtCols = 8;
+__global__ void __launch_bounds__(256) spconv_fgms_simt_kernel(const SpconvArgs a, const float *__restrict__ W, int64_t w_sc,
+                                                               int64_t w_sn, int64_t w_sk) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int groups_per_tile = kTileM / kSimtPairs;
+  const int n_tiles = a.n_map_tiles + a.n_id_tiles;
+  const int tile = warp_global / groups_per_tile, g = warp_global % groups_per_tile;
+  if (tile >= n_tiles) return;
+  int k, in_row[kSimtPairs], out_row[kSimtPairs];
+  if (tile < a.n_map_tiles) {
+    const int q0 = tile * kTileM;
+    k = upper_bound_i32(a.qkpos, a.k_vol + 1, q0) - 1;
+    const int p0 = q0 - __ldg(a.qkpos + k) + __ldg(a.kpos + k) + g * kSimtPairs, pe = __ldg(a.kpos + k + 1);
+#pragma unroll
+    for (int i = 0; i < kSimtPairs; i++) {
+      in_row[i] = p0 + i < pe ? __ldg(a.imap + p0 + i) : -1;
+      out_row[i] = p0 + i < pe ? __ldg(a.omap + p0 + i) : -1;
+    }
+  } else {
+    k = a.mid_k;
+    const int r0 = (tile - a.n_map_tiles) * kTileM + g * kSimtPairs;
+#pragma unroll
+    for (int i = 0; i < kSimtPairs; i++) in_row[i] = out_row[i] = r0 + i < a.id_rows ? r0 + i : -1;
+  }
+  if (in_row[0] < 0) return;
+  const float *Wk = W + (int64_t)k * w_sk;
+  for (int nb = 0; nb < a.c_out; nb += 32 * kSimtCols) {
+    float acc[kSimtPairs][kSimtCols];
+#pragma unroll
+    for (int i = 0; i < kSimtPairs; i++)
+#pragma unroll
+      for (int j = 0; j < kSimtCols; j++) acc[i][j] = 0.0f;
+    for (int ci = 0; ci < a.c_in; ci++) {
+      float x[kSimtPairs], w[kSimtCols];
+#pragma unroll
+      for (int i = 0; i < kSimtPairs; i++) x[i] = in_row[i] >= 0 ? __ldg(a.in + (int64_t)in_row[i] * a.ld_in + ci) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < kSimtCols; j++) {
+        const int co = nb + j * 32 + lane;
+        w[j] = co < a.c_out ? __ldg(Wk + (int64_t)ci * w_sc + (int64_t)co * w_sn) : 0.0f;
+      }
+#pragma unroll
+      for (int i = 0; i < kSimtPairs; i++)
+#pragma unroll
+        for (int j = 0; j < kSimtCols; j++) acc[i][j] = fmaf(x[i], w[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < kSimtPairs; i++) {
+      if (out_row[i] < 0) continue;
+#pragma unroll
+      for (int j = 0; j < kSimtCols; j++) {
+        const int co = nb + j * 32 + lane;
+        if (co < a.c_out) atomicAdd(a.out + (int64_t)out_row[i] * a.ld_out + co, acc[i][j]);
+      }
+    }
+  }
+}
+
+// ---- kernel gradient: dW[k][ci][co] = sum over the pairs p of offset k of in[imap[p]][ci] * dout[omap[p]][co] ----------
+// (_fgms_fusion_tf32_I_transpose of the reference, src/cuda/spconv_cuda.cu:241-247.)  A CTA of 16 x 16 threads owns a
+// 64 x 64 block of dW and a run of pair tiles; per tile it stages the gathered 128 x 64 panels of `in` and `dout` in
+// shared memory, every thread accumulates a 4 x 4 register block over the 128 pairs, and the block is flushed with
+// atomics only when the offset changes (or the run ends).  Exact fp32 FMA.
+constexpr int kWgBlk = 64;
+__global__ void __launch_bounds__(256) spconv_wgrad_kernel(const SpconvArgs a, const float *__restrict__ dout, int64_t ld_dout,
+                                                           float *__restrict__ dW) {
+  extern __shared__ uint8_t smem_raw[];
+  float *sX = reinterpret_cast<float *>(smem_raw);          // [128][64]
+  float *sG = sX + kTileM * kWgBlk;                         // [128][64]
+  __shared__ int s_in[kTileM], s_out[kTileM];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int ci0 = blockIdx.y * kWgBlk, co0 = blockIdx.z * kWgBlk;
+  const int n_tiles = a.n_map_tiles + a.n_id_tiles;
+  const int t_begin = blockIdx.x * a.tiles_per_cta, t_end = min(n_tiles, t_begin + a.tiles_per_cta);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+  int cur_k = -1;
+
+  auto flush = [&](int k) {
+    float *wk = dW + (int64_t)k * a.c_in * a.c_out;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int ci = ci0 + ty * 4 + i;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int co = co0 + tx * 4 + j;
+        if (ci < a.c_in && co < a.c_out && acc[i][j] != 0.0f) atomicAdd(wk + (int64_t)ci * a.c_out + co, acc[i][j]);
+        acc[i][j] = 0.0f;
+      }
+    }
+  };
+
+  for (int tile = t_begin; tile < t_end; tile++) {
+    int k;
+    if (tile < a.n_map_tiles) {
+      const int q0 = tile * kTileM;
+      k = upper_bound_i32(a.qkpos, a.k_vol + 1, q0) - 1;
+      if (tid < kTileM) {
+        const int p = q0 - __ldg(a.qkpos + k) + __ldg(a.kpos + k) + tid;
+        const bool ok = p < __ldg(a.kpos + k + 1);
+        s_in[tid] = ok ? __ldg(a.imap + p) : -1;
+        s_out[tid] = ok ? __ldg(a.omap + p) : -1;
+      }
+    } else {
+      k = a.mid_k;
+      if (tid < kTileM) {
+        const int r = (tile - a.n_map_tiles) * kTileM + tid;
+        s_in[tid] = s_out[tid] = r < a.id_rows ? r : -1;
+      }
+    }
+    if (k != cur_k) {
+      if (cur_k >= 0) flush(cur_k);
+      cur_k = k;
+    }
+    __syncthreads();
+    // stage the two panels: 16 lanes x float (coalesced 64-float rows), zero for padding rows / channels
+    for (int idx = tid; idx < kTileM * kWgBlk; idx += 256) {
+      const int r = idx >> 6, c = idx & 63;
+      const int ir = s_in[r], orow = s_out[r];
+      sX[idx] = (ir >= 0 && ci0 + c < a.c_in) ? __ldg(a.in + (int64_t)ir * a.ld_in + ci0 + c) : 0.0f;
+      sG[idx] = (orow >= 0 && co0 + c < a.c_out) ? __ldg(dout + (int64_t)orow * ld_dout + co0 + c) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int p = 0; p < kTileM; p++) {
+      const float4 x = *reinterpret_cast<const float4 *>(sX + p * kWgBlk + ty * 4);
+      const float4 g = *reinterpret_cast<const float4 *>(sG + p * kWgBlk + tx * 4);
+      const float xs[4] = {x.x, x.y, x.z, x.w}, gs[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(xs[i], gs[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  if (cur_k >= 0) flush(cur_k);
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct TcGeometry {
+  int n_atoms, k_pad, NT, grid_y, n_rows_pad, tmem_cols, esize;
+  size_t smem_bytes;
+};
+
+TcGeometry tc_geometry(int kdim, int ndim, int precision) {
+  TcGeometry g;
+  const int epa = precision == SPCONV_BF16 ? 64 : 32;
+  g.esize = precision == SPCONV_BF16 ? 2 : 4;
+  g.n_atoms = (kdim + epa - 1) / epa;
+  g.k_pad = g.n_atoms * epa;
+  const int n16 = round_up(ndim, 16);
+  g.NT = n16 <= kMaxNT ? n16 : kMaxNT;
+  g.grid_y = (n16 + g.NT - 1) / g.NT;
+  g.n_rows_pad = g.grid_y * g.NT;
+  g.tmem_cols = 32;
+  while (g.tmem_cols < g.NT) g.tmem_cols *= 2;
+  const int ga = g.n_atoms < kMaxAtomsPerGroup ? g.n_atoms : kMaxAtomsPerGroup;
+  g.smem_bytes = 1024 + (size_t)ga * kTileM * kAtomBytes + (size_t)ga * g.NT * kAtomBytes;
+  return g;
+}
+
+}  // namespace
+
+size_t spconv_workspace_bytes(int k_vol, int c_in, int c_out, int precision) {
+  if (precision == SPCONV_FP32) return 256;
+  // large enough for the forward (K = c_in, N = c_out) and the dX backward (K = c_out, N = c_in)
+  const TcGeometry f = tc_geometry(c_in, c_out, precision), b = tc_geometry(c_out, c_in, precision);
+  const size_t wf = (size_t)k_vol * f.n_rows_pad * f.k_pad * f.esize, wb = (size_t)k_vol * b.n_rows_pad * b.k_pad * b.esize;
+  return (wf > wb ? wf : wb) + 256;
+}
+
+cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (p.k_vol <= 0 || p.kdim <= 0 || p.ndim <= 0) return cudaErrorInvalidValue;
+  if (p.precision != SPCONV_FP32 && p.precision != SPCONV_TF32 && p.precision != SPCONV_BF16) return cudaErrorInvalidValue;
+  if (p.sum_nnz % kTileM != 0) return cudaErrorInvalidValue;   // qkpos must be quantised to 128 (q of the reference)
+  cudaError_t e;
+  if (!p.accumulate && p.out_rows > 0) {
+    if (p.ld_out == p.ndim) {
+      if ((e = cudaMemsetAsync(p.out, 0, sizeof(float) * (size_t)p.out_rows * p.ndim, stream)) != cudaSuccess) return e;
+    } else if ((e = cudaMemset2DAsync(p.out, sizeof(float) * p.ld_out, 0, sizeof(float) * p.ndim, p.out_rows, stream)) != cudaSuccess) {
+      return e;
+    }
+  }
+  SpconvArgs a;
+  a.kpos = p.kpos; a.qkpos = p.qkpos; a.imap = p.imap; a.omap = p.omap;
+  a.in = p.in; a.out = p.out; a.ld_in = p.ld_in; a.ld_out = p.ld_out;
+  a.k_vol = p.k_vol; a.c_in = p.kdim; a.c_out = p.ndim;
+  a.n_map_tiles = (int)(p.sum_nnz / kTileM);
+  a.mid_k = (p.k_vol % 2 == 1) ? p.k_vol / 2 : 0;   // src/cuda/spconv_cuda.cu:35
+  a.id_rows = p.separate_mid ? p.in_rows : 0;
+  a.n_id_tiles = (a.id_rows + kTileM - 1) / kTileM;
+  const int n_tiles = a.n_map_tiles + a.n_id_tiles;
+  if (n_tiles == 0) return cudaSuccess;
+  ProfileScope prof(5, stream);
+
+  // tensor path needs 16-byte aligned rows; otherwise (or when asked) the exact SIMT kernel
+  const bool tc_ok = p.kdim % 4 == 0 && p.ndim % 4 == 0 && p.ld_in % 4 == 0 && p.ld_out % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+  if (p.precision == SPCONV_FP32 || !tc_ok) {
+    a.Wt = nullptr; a.n_atoms = 0; a.n_rows_pad = 0; a.NT = 0; a.tmem_cols = 0; a.tiles_per_cta = 1;
+    const int64_t warps = (int64_t)n_tiles * (kTileM / kSimtPairs);
+    const int blocks = (int)((warps * 32 + 255) / 256);
+    spconv_fgms_simt_kernel<<<blocks, 256, 0, stream>>>(a, p.W, p.w_sc, p.w_sn, p.w_sk);
+    return cudaGetLastError();
+  }
+
+  const TcGeometry g = tc_geometry(p.kdim, p.ndim, p.precision);
+  const size_t w_bytes = (size_t)p.k_vol * g.n_rows_pad * g.k_pad * g.esize;
+  if (workspace == nullptr || workspace_bytes < w_bytes + 256) return cudaErrorInvalidValue;
+  uint8_t *Wt = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  const int64_t total = (int64_t)p.k_vol * g.n_rows_pad * g.k_pad;
+  const int prep_blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  if (p.precision == SPCONV_TF32)
+    spconv_prep_weights_kernel<0><<<prep_blocks, 256, 0, stream>>>(p.W, Wt, p.k_vol, p.kdim, p.ndim, g.k_pad, g.n_rows_pad, p.w_sc, p.w_sn, p.w_sk);
+  else
+    spconv_prep_weights_kernel<1><<<prep_blocks, 256, 0, stream>>>(p.W, Wt, p.k_vol, p.kdim, p.ndim, g.k_pad, g.n_rows_pad, p.w_sc, p.w_sn, p.w_sk);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+  a.Wt = Wt; a.n_atoms = g.n_atoms; a.n_rows_pad = g.n_rows_pad; a.NT = g.NT; a.tmem_cols = g.tmem_cols;
+  // a run of tiles per CTA amortises the W[k] panel; keep >= ~8 CTAs per SM in flight for latency hiding
+  const int sms = device_sm_count();
+  int tpc = n_tiles / (sms * 8);
+  if (tpc < 1) tpc = 1;
+  if (tpc > 8) tpc = 8;
+  a.tiles_per_cta = tpc;
+  dim3 grid((n_tiles + tpc - 1) / tpc, g.grid_y);
+  if (p.precision == SPCONV_TF32) {
+    if ((e = cudaFuncSetAttribute(spconv_fgms_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes)) != cudaSuccess) return e;
+    spconv_fgms_tc_kernel<0><<<grid, 128, g.smem_bytes, stream>>>(a);
+  } else {
+    if ((e = cudaFuncSetAttribute(spconv_fgms_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes)) != cudaSuccess) return e;
+    spconv_fgms_tc_kernel<1><<<grid, 128, g.smem_bytes, stream>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t spconv_wgrad(int k_vol, int c_in, int c_out, const int *kpos, const int *qkpos, const int *imap, const int *omap,
+                         int64_t sum_nnz, const float *in, int64_t ld_in, int in_rows, const float *dout, int64_t ld_dout,
+                         float *dW, int precision, int separate_mid, cudaStream_t stream) {
+  (void)precision;   // fp32 FMA for every precision: the gradient of the weights is the small, accuracy-critical output
+  if (k_vol <= 0 || c_in <= 0 || c_out <= 0 || sum_nnz % kTileM != 0) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)k_vol * c_in * c_out, stream);
+  if (e != cudaSuccess) return e;
+  SpconvArgs a{};
+  a.kpos = kpos; a.qkpos = qkpos; a.imap = imap; a.omap = omap; a.in = in; a.ld_in = ld_in;
+  a.k_vol = k_vol; a.c_in = c_in; a.c_out = c_out;
+  a.n_map_tiles = (int)(sum_nnz / kTileM);
+  a.mid_k = (k_vol % 2 == 1) ? k_vol / 2 : 0;
+  a.id_rows = separate_mid ? in_rows : 0;
+  a.n_id_tiles = (a.id_rows + kTileM - 1) / kTileM;
+  const int n_tiles = a.n_map_tiles + a.n_id_tiles;
+  if (n_tiles == 0) return cudaSuccess;
+  ProfileScope prof(6, stream);
+  const int by = (c_in + kWgBlk - 1) / kWgBlk, bz = (c_out + kWgBlk - 1) / kWgBlk;
+  int tpc = n_tiles * by * bz / (device_sm_count() * 6);
+  if (tpc < 1) tpc = 1;
+  if (tpc > 16) tpc = 16;
+  a.tiles_per_cta = tpc;
+  const size_t smem = sizeof(float) * 2 * kTileM * kWgBlk;
+  if ((e = cudaFuncSetAttribute(spconv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  dim3 grid((n_tiles + tpc - 1) / tpc, by, bz);
+  spconv_wgrad_kernel<<<grid, 256, smem, stream>>>(a, dout, ld_dout, dW);
+  return cudaGetLastError();
+}
+
+}  // namespace dgs

@@ -15,6 +15,7 @@ _vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_s
 
 SUM, MAX, MIN, MEAN = 0, 1, 2, 3                    # include/gspmm.h:13
 ADD, SUB, MUL, DIV, COPY, MASKMUL = 0, 1, 2, 3, 4, 5  # include/gspmm.h:14 (+ COPY / MASKMUL)
+SPCONV_FP32, SPCONV_TF32, SPCONV_BF16 = 0, 1, 2       # include/dgsparse_b200.h dgsSpconvPrecision
 
 # every symbol include/*.h declares: (restype, argtypes)
 SIGNATURES = {
@@ -31,6 +32,10 @@ SIGNATURES = {
     "dgs_csr2csc_workspace_bytes": (_sz, [_i32, _i32, _i64]),
     "dgs_csr2csc": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgs_edge_softmax": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp]),
+    "dgs_spconv_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "dgs_spconv_fwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
+    "dgs_spconv_bwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+                              _vp, _sz, _vp]),
     "dgs_ipc_export": (_i32, [_vp, _vp, ctypes.POINTER(_i64)]),
     "dgs_ipc_open": (_i32, [_vp, ctypes.POINTER(_vp)]),
     "dgs_ipc_close": (_i32, [_vp]),

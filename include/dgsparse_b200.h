@@ -70,6 +70,30 @@ int dgs_csr2csc(int M, int ncols, int64_t nnz, const int *rowptr, const int *col
 /* Per row and head: softmax over the row's nonzeros of values[p*head + h] (see dgsparse.h). */
 int dgs_edge_softmax(int M, int head, const int *rowptr, const float *values, float *out, void *stream);
 
+/* Sparse 3-D convolution, fused gather-GEMM-scatter (the reference's unbuilt torch.ops.dgsparse_spconv.spconv,
+ * src/spconv.cpp:18-74; spconv_fwd_fused / spconv_bwd_fused, src/cuda/spconv_cuda.cu:18-253):
+ *   forward   out_feats[out_map[p], :] += in_feats[in_map[p], :] @ kernel[k]     p in [kpos[k], kpos[k+1])
+ *   backward  in_grad[in_map[p], :]    += out_grad[out_map[p], :] @ kernel[k]^T
+ *             kernel_grad[k]           += in_feats[in_map[p], :]^T (x) out_grad[out_map[p], :]
+ * in_feats [in_nnz, c_in], kernel [k_vol, c_in, c_out], out_feats [out_nnz, c_out], all fp32 row-major contiguous.
+ * kpos / qkpos: device int32 [k_vol + 1]; qkpos = kpos with every offset's count rounded up to a multiple of 128
+ * (test/test_spconv.py:5-14), sum_nnz = qkpos[k_vol].  separate_mid != 0: the centre offset (k_vol / 2) is NOT in
+ * the maps and is applied to the identity map (needs in_nnz == out_nnz), spconv_cuda.cu:52-78.
+ * precision: DGS_SPCONV_FP32 = exact fp32 FMA (the reference's arch80 = false kernels), DGS_SPCONV_TF32 = tcgen05
+ * kind::tf32 with fp32 accumulation in TMEM (arch80 = true), DGS_SPCONV_BF16 = tcgen05 kind::f16 on bf16-rounded
+ * operands.  Outputs are fully overwritten (the reference leaves out_feats uninitialised).
+ * in_grad or kernel_grad may be NULL to skip that half of the backward.  kernel_grad is always fp32 FMA. */
+enum dgsSpconvPrecision { DGS_SPCONV_FP32 = 0, DGS_SPCONV_TF32 = 1, DGS_SPCONV_BF16 = 2 };
+size_t dgs_spconv_workspace_bytes(int k_vol, int c_in, int c_out, int precision);
+int dgs_spconv_fwd(int in_nnz, int out_nnz, int k_vol, int c_in, int c_out, const int *kpos, const int *qkpos,
+                   const int *in_map, const int *out_map, int64_t sum_nnz, const float *in_feats, const float *kernel,
+                   float *out_feats, int separate_mid, int precision, void *workspace, size_t workspace_bytes,
+                   void *stream);
+int dgs_spconv_bwd(int in_nnz, int out_nnz, int k_vol, int c_in, int c_out, const int *kpos, const int *qkpos,
+                   const int *in_map, const int *out_map, int64_t sum_nnz, const float *out_grad, const float *in_feats,
+                   const float *kernel, float *in_grad, float *kernel_grad, int separate_mid, int precision,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
 /* Peer memory for the fused column-shard epilogue: export a device allocation to the other ranks of
  * the box (CUDA IPC), open theirs; the opened base + offset is passed in dst[] of dgs_spmm_csr_multi. */
 int dgs_ipc_export(const void *dptr, void *handle64, int64_t *offset);
@@ -79,7 +103,7 @@ int dgs_ipc_close(void *base);
 /* Per-launch device timing (bench.py's roofline leg): when enabled every kernel this library launches
  * is bracketed by CUDA events on its stream.  dgs_profile_collect synchronises those events and returns
  * the number of records written: kernel_ids[i] (1 = SpMM row-segment, 2 = SpMM fix-up, 3 = SDDMM,
- * 4 = csr2csc passes, 5 = spconv) and ms[i]; it then clears the list. */
+ * 4 = csr2csc passes, 5 = spconv gather-GEMM-scatter, 6 = spconv kernel gradient) and ms[i]; it then clears the list. */
 int dgs_profile_enable(int on);
 int dgs_profile_collect(int max_records, int *kernel_ids, float *ms);
 

@@ -14,6 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE_SO = os.path.join(_HERE, "_build", "liboracle.so")
 _REF_SO = os.path.join(_HERE, "_ref", "libref_host.so")
+_REF_CUDA_SO = os.path.join(_HERE, "_ref", "libref_cuda.so")
 
 REDUCE = {"sum": 0, "max": 1, "min": 2, "mean": 3}            # include/gspmm.h:13
 COMPUTE = {"add": 0, "sub": 1, "mul": 2, "div": 3, "copy": 4}  # include/gspmm.h:14 (+copy)
@@ -31,6 +32,9 @@ def build(force=False):
     if os.path.exists("/root/reference/example/util/sp_util.hpp") and (
             force or not os.path.exists(_REF_SO)):
         subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    if os.path.exists("/root/reference/src/ge-spmm/gespmm.cc") and (
+            force or not os.path.exists(_REF_CUDA_SO)):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "refcuda"])
 
 
 def _p(a, typ):
@@ -75,6 +79,44 @@ def ref_lib():
             if os.path.exists(_REF_SO):
                 _ref = ctypes.CDLL(_REF_SO)
         return _ref
+
+
+_ref_cuda = None
+
+
+class SpMatCsrDescr(ctypes.Structure):
+    """struct SpMatCsrDescr_t of the reference, src/ge-spmm/gespmm.h:9-16 (passed by value)."""
+    _fields_ = [("nrow", ctypes.c_int), ("ncol", ctypes.c_int), ("nnz", ctypes.c_int),
+                ("indptr", ctypes.c_void_p), ("indices", ctypes.c_void_p), ("data", ctypes.c_void_p)]
+
+
+def ref_cuda_lib():
+    """The reference's own CUDA C ABI compiled for sm_100a (oracle/_ref/libref_cuda.so) or None.
+
+    Device-pointer entry points, all launching on the legacy default stream and returning void:
+      spmm_cuda(m, N, rowptr, col, val, B, C)               src/ge-spmm/gespmm.cc:114-123
+      spmm_cuda_no_edge_value(m, N, rowptr, col, _, B, C)    src/ge-spmm/gespmm.cc:125-134
+      gespmmCsrSpMM(SpMatCsrDescr_t, B, N, C, transpose, alg) src/ge-spmm/gespmm.cc:29-111
+      sddmm_cuda_csr(m, k, nnz, rowptr, col, D1, D2, out)    src/sddmm/sddmm.cu:25-41
+      sddmm_cuda_coo(k, nnz, row, col, D1, D2, out)          src/sddmm/sddmm.cu:8-23
+    """
+    global _ref_cuda
+    with _lock:
+        if _ref_cuda is None and os.path.exists(_REF_CUDA_SO):
+            L = ctypes.CDLL(_REF_CUDA_SO)
+            vp, ci = ctypes.c_void_p, ctypes.c_int
+            L.spmm_cuda.argtypes = [ci, ci, vp, vp, vp, vp, vp]
+            L.spmm_cuda.restype = None
+            L.spmm_cuda_no_edge_value.argtypes = [ci, ci, vp, vp, vp, vp, vp]
+            L.spmm_cuda_no_edge_value.restype = None
+            L.gespmmCsrSpMM.argtypes = [SpMatCsrDescr, vp, ci, vp, ctypes.c_bool, ci]
+            L.gespmmCsrSpMM.restype = None
+            L.sddmm_cuda_csr.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp]
+            L.sddmm_cuda_csr.restype = None
+            L.sddmm_cuda_coo.argtypes = [ci, ci, vp, vp, vp, vp, vp]
+            L.sddmm_cuda_coo.restype = None
+            _ref_cuda = L
+        return _ref_cuda
 
 
 def num_threads():
