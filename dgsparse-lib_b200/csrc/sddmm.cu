@@ -15,6 +15,7 @@
 // U=8 edges are processed together: their D2 rows are requested back-to-back, the D1 row is shared
 // when the 8 edges lie in one CSR row, and the 8 partial dots are reduced with a transposing shuffle
 // tree (7 + log2(G/8) shuffles for 8 edges instead of 8*log2(G)); results are stored coalesced.
+#include <cstdlib>
 #include "common.cuh"
 #include "spmm.h"
 
@@ -184,6 +185,213 @@ __global__ void __launch_bounds__(kSdThreads) sddmm_kernel(const SddmmArgs a) {
   }
 }
 
+
+// ---- shared-memory ring variant (rows of 512 B .. 4 KB) ---------------------------------------------------------------
+// A random 1 KB-row gather is latency bound: the register-staged kernel above holds its loads in 112 registers, sits
+// at 20 % warp occupancy and leaves every warp on long-scoreboard.  Here the operand rows go global -> shared with
+// cp.async (LDGSTS, 16 B per lane, no data registers): a warp keeps STAGES-1 batches of NB edges (NB D2 rows + the
+// distinct D1 rows among them) in flight in its own shared-memory ring while it consumes the oldest batch.
+// Index math is done one edge per LANE for 32 edges at a time (column load, CSR row search in a rowptr window,
+// source pointers, D1-row de-duplication by ballot) and broadcast with shuffles, so the per-edge instruction stream
+// is shuffle + address add + cp.async and the consumer is LDS + FMA with the edges of a batch independent (ILP).
+// (Measured dead ends, profiles/README.md: cp.async.bulk/UBLKCP, one 1 KB bulk copy per row, ran 2.3x slower — the
+// TMA unit serialises small random copies; the first cp.async ring did its index math serially per edge and was
+// instruction-latency bound, time inversely proportional to the warp count.)
+// D1 rows are streamed once -> L2 evict_first policy; D2 rows are the reused operand and keep the default policy
+// (a fractional evict_last policy on D2, 0.3 .. 0.9 of L2, was measured and changed nothing: 0.198 - 0.205 ms).
+constexpr int kRgNB = 4;          // edges per batch: one per 8-lane group of the copying warp
+constexpr int kRgBPS = 32 / kRgNB; // batches per 32-edge superbatch
+constexpr int kRgMetaBytes = 2 * kRgBPS * 4 + 2 * 32 * 4;   // two superbatches of packed slots + degrees
+
+__device__ __forceinline__ uint32_t sd_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sd_cp16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void sd_cp16_hint(uint32_t dst, const void *src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ const char *sd_shfl_ptr(const char *p, int src_lane) {
+  unsigned long long v = reinterpret_cast<unsigned long long>(p);
+  unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src_lane), hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src_lane);
+  return reinterpret_cast<const char *>(((unsigned long long)hi << 32) | lo);
+}
+
+struct SddmmRingArgs {
+  SddmmArgs a;
+  int wpc;             // warps per CTA
+  uint32_t slot_bytes; // K*4 rounded up to 128
+  uint32_t warp_bytes; // shared memory per warp
+};
+
+// KCH = ceil(K / 128): 16-byte chunks per lane and row in the consumer; FULLK: K == 128 * KCH (no column predicates)
+template <int KCH, int STAGES, bool FULLK, bool COO, bool MEAN>
+__global__ void __launch_bounds__(512, 1) sddmm_ring_kernel(const SddmmRingArgs g) {
+  extern __shared__ __align__(128) uint8_t sd_smem[];
+  constexpr int NB = kRgNB, BPS = kRgBPS;
+  constexpr int SEGS = KCH * 4;   // 128-byte segments per row: one per copy instruction of an 8-lane group
+  const SddmmArgs &a = g.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = lane >> 3, ql = lane & 7;
+  const uint32_t rowbytes = (uint32_t)a.K * 4u;
+  // per-warp carve-up: [STAGES][2*NB] row slots | packed D1 slots per batch [2][BPS] | degree per edge [2][32]
+  uint8_t *wbase = sd_smem + (size_t)warp * g.warp_bytes;
+  const uint32_t rows_u32 = sd_smem_u32(wbase);
+  const uint32_t stage_bytes = 2u * NB * g.slot_bytes;
+  int *s_slots = reinterpret_cast<int *>(wbase + (size_t)STAGES * stage_bytes);
+  int *s_deg = s_slots + 2 * BPS;
+  uint64_t pol_stream;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+
+  const int chunk_id = blockIdx.x * g.wpc + warp;
+  if (chunk_id >= a.num_chunks) return;
+  const int lo = chunk_id * a.chunk;
+  const int hi = (a.nnz - lo <= a.chunk) ? a.nnz : lo + a.chunk;
+  const int nb_total = (hi - lo + NB - 1) / NB;
+
+  int r_hint = COO ? 0 : row_of_nnz(a.rowptr, a.M, lo);   // row of the superbatch's first edge (uniform)
+  bool in_k[KCH];
+#pragma unroll
+  for (int j = 0; j < KCH; j++) in_k[j] = FULLK || (lane + 32 * j) * 4 < a.K;
+
+  // ---- per-lane state of the current superbatch: lane u <-> edge min(lo + 32*sb + u, hi - 1) ----
+  // (edges past the segment end are clamped to its last edge: they are fetched and multiplied like the others and
+  //  simply not stored, which keeps every batch full and the inner loops free of validity branches)
+  const char *my_src2 = nullptr, *my_src1 = nullptr;   // base of this edge's D2 / D1 row
+  unsigned new_mask = 0;                               // bit u: edge u opens a new D1 slot in its batch (uniform)
+
+  auto load_super = [&](int sb) {
+    const int pos = min(lo + sb * 32 + lane, hi - 1);
+    const int c = __ldcs(a.col + pos);
+    int rr, deg = 1;
+    if (COO) {
+      rr = __ldcs(a.row + pos);
+    } else {
+      // first idx in (r_hint, M] with rowptr[idx] > pos; try a 32-row window first, else the whole tail
+      int l = r_hint + 1, h = min(a.M, r_hint + 32);
+      if (__ldg(a.rowptr + h) <= pos) { l = h + 1; h = a.M; }
+      while (l < h) {
+        const int mid = (l + h) >> 1;
+        if (__ldg(a.rowptr + mid) > pos) h = mid; else l = mid + 1;
+      }
+      rr = l - 1;
+      if (MEAN) deg = __ldg(a.rowptr + rr + 1) - __ldg(a.rowptr + rr);
+    }
+    my_src2 = reinterpret_cast<const char *>(a.D2 + (size_t)c * a.ld2);
+    my_src1 = reinterpret_cast<const char *>(a.D1 + (size_t)rr * a.ld1);
+    const int prev = __shfl_up_sync(0xffffffffu, rr, 1);
+    new_mask = __ballot_sync(0xffffffffu, (lane % NB) == 0 || rr != prev);
+    if ((lane % NB) == 0) {   // D1 slot of each edge of the batch, 4 bits each: running count of "new" flags
+      const unsigned gb = (new_mask >> lane) & 15u;
+      const int s1 = (gb >> 1) & 1, s2 = s1 + ((gb >> 2) & 1), s3 = s2 + ((gb >> 3) & 1);
+      s_slots[(sb & 1) * BPS + lane / NB] = (s1 << 4) | (s2 << 8) | (s3 << 12);
+    }
+    if (MEAN) s_deg[(sb & 1) * 32 + lane] = deg;
+    if (!COO) r_hint = __shfl_sync(0xffffffffu, rr, 31);   // rows are monotone: the next superbatch searches from here
+  };
+
+  auto issue = [&](int b) {   // always commits exactly one cp.async group (possibly empty)
+    if (b < nb_total) {
+      if (b % BPS == 0) load_super(b / BPS);
+      const int u0 = (b % BPS) * NB;
+      const unsigned gb = (new_mask >> u0) & 15u;
+      // 8-lane group q fetches edge u0 + q: its D2 row, and its D1 row when that edge opens a new slot
+      const char *p2 = sd_shfl_ptr(my_src2, u0 + q) + ql * 16;
+      const char *p1 = sd_shfl_ptr(my_src1, u0 + q) + ql * 16;
+      const uint32_t sbase = rows_u32 + (uint32_t)(b % STAGES) * stage_bytes + (uint32_t)ql * 16u;
+      const uint32_t dst2 = sbase + (uint32_t)q * g.slot_bytes;
+#pragma unroll
+      for (int i = 0; i < SEGS; i++)
+        if (FULLK || i * 128u + ql * 16u < rowbytes) sd_cp16(dst2 + 128u * i, p2 + 128 * i);
+      if ((gb >> q) & 1u) {
+        const uint32_t dst1 = sbase + (uint32_t)(NB + __popc(gb & ((2u << q) - 1u)) - 1) * g.slot_bytes;
+#pragma unroll
+        for (int i = 0; i < SEGS; i++)
+          if (FULLK || i * 128u + ql * 16u < rowbytes) sd_cp16_hint(dst1 + 128u * i, p1 + 128 * i, pol_stream);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int myslot = edge_slot<32, NB>(lane);
+  const bool writer = (lane & (32 / NB - 1)) == 0;
+
+#pragma unroll
+  for (int b = 0; b < STAGES - 1; b++) issue(b);
+  for (int b = 0; b < nb_total; b++) {
+    issue(b + STAGES - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");   // this lane's copies of batch b landed
+    __syncwarp();                                                            // ... and every other lane's
+    const uint8_t *srows = wbase + (size_t)(b % STAGES) * stage_bytes;
+    const int mi = ((b / BPS) & 1) * BPS + (b % BPS);
+    const int packed = s_slots[mi];
+    float4 y[NB][KCH];
+#pragma unroll
+    for (int e = 0; e < NB; e++) {
+      const float4 *yr = reinterpret_cast<const float4 *>(srows + (size_t)e * g.slot_bytes);
+#pragma unroll
+      for (int j = 0; j < KCH; j++)
+        if (in_k[j]) y[e][j] = yr[lane + 32 * j];
+    }
+    float p[NB];
+    float4 x[KCH];
+#pragma unroll
+    for (int e = 0; e < NB; e++) {
+      const int d1 = (packed >> (4 * e)) & 15;
+      if (e == 0 || d1 != ((packed >> (4 * (e - 1))) & 15)) {   // uniform: the D1 row changes with this edge
+        const float4 *xr = reinterpret_cast<const float4 *>(srows + (size_t)(NB + d1) * g.slot_bytes);
+#pragma unroll
+        for (int j = 0; j < KCH; j++)
+          if (in_k[j]) x[j] = xr[lane + 32 * j];
+      }
+      float acc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < KCH; j++) {
+        if (in_k[j]) {
+          acc += x[j].x * y[e][j].x;
+          acc += x[j].y * y[e][j].y;
+          acc += x[j].z * y[e][j].z;
+          acc += x[j].w * y[e][j].w;
+        }
+      }
+      p[e] = acc;
+    }
+    group_multi_reduce<32, NB>(p, lane, 0xffffffffu);
+    const int pos = lo + b * NB + myslot;
+    if (writer && pos < hi) {
+      float res = p[0];
+      if (MEAN) {
+        const int deg = s_deg[((b / BPS) & 1) * 32 + (b % BPS) * NB + myslot];
+        if (deg > 0) res /= (float)deg;
+      }
+      __stcs(a.out + pos, res);
+    }
+    __syncwarp();   // every lane is done with this stage's rows before it is refilled
+  }
+}
+
+template <int KCH, int STAGES>
+static cudaError_t launch_ring(const SddmmRingArgs &g, int grid, size_t smem, bool coo, bool mean, cudaStream_t s) {
+  cudaError_t e;
+  const bool fullk = g.a.K == 128 * KCH;
+#define DGS_RING(FULL_, COO_, MEAN_)                                                                                       \
+  do {                                                                                                                     \
+    if ((e = cudaFuncSetAttribute(sddmm_ring_kernel<KCH, STAGES, FULL_, COO_, MEAN_>,                                      \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;       \
+    sddmm_ring_kernel<KCH, STAGES, FULL_, COO_, MEAN_><<<grid, g.wpc * 32, smem, s>>>(g);                                  \
+  } while (0)
+  if (fullk) {
+    if (coo) DGS_RING(true, true, false);
+    else if (mean) DGS_RING(true, false, true);
+    else DGS_RING(true, false, false);
+  } else {
+    if (coo) DGS_RING(false, true, false);
+    else if (mean) DGS_RING(false, false, true);
+    else DGS_RING(false, false, false);
+  }
+#undef DGS_RING
+  return cudaGetLastError();
+}
+
 template <int VEC, int G>
 static cudaError_t launch_g(const SddmmArgs &a, bool coo, bool mean, bool mask, cudaStream_t s) {
   const int gpb = kSdThreads / G;
@@ -212,6 +420,46 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
   auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   const bool vec4 = (p.K % 4 == 0) && (p.ld1 % 4 == 0) && (p.ld2 % 4 == 0) && al16(p.D1) && al16(p.D2) &&
                     (!mask || al16(p.E));
+  // rows of 512 B .. 4 KB made of aligned 16-byte chunks: shared-memory ring kernel
+  if (vec4 && !mask && p.K >= 128 && p.K <= 1024 && !getenv("DGS_SDDMM_NO_RING")) {
+    SddmmRingArgs g;
+    SddmmArgs &a = g.a;
+    a.M = p.M; a.K = p.K; a.nnz = (int)p.nnz;
+    a.rowptr = p.rowptr; a.row = p.row; a.col = p.col;
+    a.D1 = p.D1; a.D2 = p.D2; a.ld1 = p.ld1; a.ld2 = p.ld2;
+    a.E = nullptr; a.out = p.out;
+    g.slot_bytes = ((uint32_t)p.K * 4u + 127u) & ~127u;
+    // ring geometry: 4 edges per batch, STAGES batches per warp ring; as many warps as ~200 KB of ring allow
+    int STAGES = 2;
+    if (const char *e = getenv("DGS_SDDMM_STAGES")) STAGES = atoi(e) == 3 ? 3 : 2;
+    g.warp_bytes = (uint32_t)STAGES * 2u * kRgNB * g.slot_bytes + (uint32_t)kRgMetaBytes;
+    g.warp_bytes = (g.warp_bytes + 127u) & ~127u;
+    int wpc = (int)((200u * 1024u) / g.warp_bytes);
+    if (wpc > 16) wpc = 16;
+    if (wpc >= 1) {
+      g.wpc = wpc;
+      const int64_t resident_warps = (int64_t)device_sm_count() * wpc;
+      int64_t chunk = (p.nnz + resident_warps * 6 - 1) / (resident_warps * 6);
+      if (chunk < 64) chunk = 64;
+      if (chunk > 8192) chunk = 8192;
+      a.chunk = (int)((chunk + 31) / 32 * 32);
+      a.num_chunks = (int)((p.nnz + a.chunk - 1) / a.chunk);
+      const int grid = (a.num_chunks + wpc - 1) / wpc;
+      const size_t smem = (size_t)wpc * g.warp_bytes;
+      const bool mean = p.mean != 0 && !coo;
+      ProfileScope prof(3, stream);
+#define DGS_RING_GEO(KCH_)                                                                    \
+  do {                                                                                        \
+    if (STAGES == 3) return launch_ring<KCH_, 3>(g, grid, smem, coo, mean, stream);           \
+    return launch_ring<KCH_, 2>(g, grid, smem, coo, mean, stream);                            \
+  } while (0)
+      if (p.K <= 128) DGS_RING_GEO(1);
+      if (p.K <= 256) DGS_RING_GEO(2);
+      if (p.K <= 512) DGS_RING_GEO(4);
+      DGS_RING_GEO(8);
+#undef DGS_RING_GEO
+    }
+  }
   int G = 4;
   const int lanes = vec4 ? (p.K + 3) / 4 : p.K;
   while (G < lanes && G < 32) G <<= 1;

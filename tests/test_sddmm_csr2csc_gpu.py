@@ -49,7 +49,7 @@ def test_sddmm_golden_k32(K, graphs, name):
     assert_close_f32(o.cpu().numpy(), g["out"], what="sddmm_cuda_coo")
 
 
-@pytest.mark.parametrize("Kd", [1, 2, 7, 16, 36, 64, 100, 256, 300])
+@pytest.mark.parametrize("Kd", [1, 2, 7, 16, 36, 64, 100, 128, 132, 200, 256, 300, 512, 640, 1024, 1028])
 def test_sddmm_widths(K, oracle, graphs, Kd):
     """Any K, including K%4==0 but K%32!=0 where the reference's vec4 CSR kernel drops the residue (q13)."""
     M, Kc = 2000, 1500
