@@ -2,6 +2,7 @@
 // include/dgsparse_b200.h (extended, stream-taking).  No torch types anywhere.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <cuda.h>
@@ -221,7 +222,10 @@ namespace {
 struct HostStage {
   void *dev = nullptr;
   size_t bytes = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // H2D copies
+  cudaStream_t s_compute = nullptr;   // kernels
+  cudaStream_t s_d2h = nullptr;       // D2H copies
+  cudaEvent_t ev_in[16] = {nullptr}, ev_done[16] = {nullptr};
   int device = -1;
 };
 thread_local HostStage g_stage;
@@ -234,6 +238,11 @@ cudaError_t stage_reserve(size_t need) {
   if (s.device != dev) {
     if (s.dev) { cudaFree(s.dev); s.dev = nullptr; s.bytes = 0; }
     if (s.stream) { cudaStreamDestroy(s.stream); s.stream = nullptr; }
+    if (s.s_compute) {
+      cudaStreamDestroy(s.s_compute); cudaStreamDestroy(s.s_d2h);
+      s.s_compute = s.s_d2h = nullptr;
+      for (int i = 0; i < 16; i++) { cudaEventDestroy(s.ev_in[i]); cudaEventDestroy(s.ev_done[i]); }
+    }
     if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
     s.device = dev;
   }
@@ -245,19 +254,60 @@ cudaError_t stage_reserve(size_t need) {
   return cudaSuccess;
 }
 inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+
+// rowptr[i] -= base for a row block copied verbatim from the host CSR (so col/val can be addressed block-relative)
+__global__ void __launch_bounds__(256) rebase_rowptr_kernel(int *rp, int n, int base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rp[i] -= base;
+}
 }  // namespace
 
 int dgs_spmm_csr_host(int M, int K, int N, int64_t nnz, const int *rowptr, const int *col, const float *val,
                       const float *B, float *C, int *E, int reduce, int compute) {
   if (M < 0 || K < 0 || N < 0 || nnz < 0) return fail(cudaErrorInvalidValue, "dgs_spmm_csr_host(sizes)");
+  if (M == 0 || N == 0) return 0;
   const bool with_arg = E != nullptr;
-  const size_t b_rowptr = up256(4 * ((size_t)M + 1)), b_col = up256(4 * (size_t)nnz), b_val = val ? b_col : 0;
+  // Row blocks of ~equal nnz, pipelined over three streams: while block i is multiplied, block i+1's CSR slice is
+  // still crossing PCIe and block i-1's rows of C are already on their way back.  B goes first (every block needs it).
+  int64_t blk_nnz = 8ll << 20;           // >= ~8 M nonzeros (64 MB of col+val) per block
+  if (const char *env = getenv("DGS_HOST_BLOCK_NNZ")) { if (atoll(env) > 0) blk_nnz = atoll(env); }
+  int nblk = (int)(nnz / blk_nnz);
+  if (nblk < 1) nblk = 1;
+  if (nblk > 16) nblk = 16;
+  if (nblk > M) nblk = M;
+  int r_begin[17];
+  r_begin[0] = 0;
+  for (int b = 1; b < nblk; b++) {   // first row whose start offset reaches the b-th nnz quantile
+    const int64_t target = nnz * b / nblk;
+    int lo = r_begin[b - 1], hi = M;
+    while (lo < hi) {
+      const int mid = lo + (hi - lo) / 2;
+      if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    r_begin[b] = lo;
+  }
+  r_begin[nblk] = M;
+  size_t ws_need = 256;
+  for (int b = 0; b < nblk; b++) {
+    const size_t w = dgs::spmm_workspace_bytes(N, (int64_t)rowptr[r_begin[b + 1]] - rowptr[r_begin[b]], with_arg);
+    if (w > ws_need) ws_need = w;
+  }
+  const size_t b_rowptr = up256(4 * ((size_t)M + 1 + nblk)), b_col = up256(4 * (size_t)nnz), b_val = val ? b_col : 0;
   const size_t b_B = up256(4 * (size_t)K * N), b_C = up256(4 * (size_t)M * N), b_E = with_arg ? b_C : 0;
-  const size_t b_ws = up256(dgs::spmm_workspace_bytes(N, nnz, with_arg));
+  const size_t b_ws = up256(ws_need);
   cudaError_t e = stage_reserve(b_rowptr + b_col + b_val + b_B + b_C + b_E + b_ws);
   if (e != cudaSuccess) return fail(e, "dgs_spmm_csr_host(alloc)");
-  char *d = static_cast<char *>(g_stage.dev);
-  cudaStream_t s = g_stage.stream;
+  HostStage &st = g_stage;
+  if (st.s_compute == nullptr) {
+    if ((e = cudaStreamCreateWithFlags(&st.s_compute, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
+    if ((e = cudaStreamCreateWithFlags(&st.s_d2h, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
+    for (int i = 0; i < 16; i++) {
+      if ((e = cudaEventCreateWithFlags(&st.ev_in[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+      if ((e = cudaEventCreateWithFlags(&st.ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+    }
+  }
+  char *d = static_cast<char *>(st.dev);
+  cudaStream_t s_in = st.stream, s_k = st.s_compute, s_out = st.s_d2h;
   int *d_rowptr = (int *)d; d += b_rowptr;
   int *d_col = (int *)d; d += b_col;
   float *d_val = val ? (float *)d : nullptr; d += b_val;
@@ -265,15 +315,34 @@ int dgs_spmm_csr_host(int M, int K, int N, int64_t nnz, const int *rowptr, const
   float *d_C = (float *)d; d += b_C;
   int *d_E = with_arg ? (int *)d : nullptr; d += b_E;
   void *d_ws = d;
-  if ((e = cudaMemcpyAsync(d_rowptr, rowptr, 4 * ((size_t)M + 1), cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, "h2d rowptr");
-  if ((e = cudaMemcpyAsync(d_col, col, 4 * (size_t)nnz, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, "h2d col");
-  if (val && (e = cudaMemcpyAsync(d_val, val, 4 * (size_t)nnz, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, "h2d val");
-  if ((e = cudaMemcpyAsync(d_B, B, 4 * (size_t)K * N, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail(e, "h2d B");
-  int rc = dgs_spmm_csr(M, N, nnz, d_rowptr, d_col, d_val, d_B, N, d_C, N, d_E, N, reduce, compute, d_ws, b_ws, s);
-  if (rc) return rc;
-  if ((e = cudaMemcpyAsync(C, d_C, 4 * (size_t)M * N, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e, "d2h C");
-  if (with_arg && (e = cudaMemcpyAsync(E, d_E, 4 * (size_t)M * N, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return fail(e, "d2h E");
-  return ok_or(cudaStreamSynchronize(s), "dgs_spmm_csr_host(sync)");
+  if ((e = cudaMemcpyAsync(d_B, B, 4 * (size_t)K * N, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return fail(e, "h2d B");
+  for (int b = 0; b < nblk; b++) {
+    const int r0 = r_begin[b], r1 = r_begin[b + 1], rows = r1 - r0;
+    const int64_t p0 = rowptr[r0], p1 = rowptr[r1], n = p1 - p0;
+    int *d_rp = d_rowptr + r0 + b;   // block b's rowptr copy holds rows + 1 entries: keep the copies disjoint
+    if ((e = cudaMemcpyAsync(d_rp, rowptr + r0, 4 * ((size_t)rows + 1), cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return fail(e, "h2d rowptr");
+    if (n > 0) {
+      if ((e = cudaMemcpyAsync(d_col + p0, col + p0, 4 * (size_t)n, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return fail(e, "h2d col");
+      if (val && (e = cudaMemcpyAsync(d_val + p0, val + p0, 4 * (size_t)n, cudaMemcpyHostToDevice, s_in)) != cudaSuccess) return fail(e, "h2d val");
+    }
+    if ((e = cudaEventRecord(st.ev_in[b], s_in)) != cudaSuccess) return fail(e, "event record");
+    if ((e = cudaStreamWaitEvent(s_k, st.ev_in[b], 0)) != cudaSuccess) return fail(e, "event wait");
+    if (rows > 0) {
+      if (p0 != 0) rebase_rowptr_kernel<<<(rows + 1 + 255) / 256, 256, 0, s_k>>>(d_rp, rows + 1, (int)p0);
+      int rc = dgs_spmm_csr(rows, N, n, d_rp, d_col + p0, d_val ? d_val + p0 : nullptr, d_B, N, d_C + (size_t)r0 * N, N,
+                            d_E ? d_E + (size_t)r0 * N : nullptr, N, reduce, compute, d_ws, b_ws, s_k);
+      if (rc) return rc;
+    }
+    if ((e = cudaEventRecord(st.ev_done[b], s_k)) != cudaSuccess) return fail(e, "event record");
+    if ((e = cudaStreamWaitEvent(s_out, st.ev_done[b], 0)) != cudaSuccess) return fail(e, "event wait");
+    if (rows > 0) {
+      if ((e = cudaMemcpyAsync(C + (size_t)r0 * N, d_C + (size_t)r0 * N, 4 * (size_t)rows * N, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) return fail(e, "d2h C");
+      if (with_arg && (e = cudaMemcpyAsync(E + (size_t)r0 * N, d_E + (size_t)r0 * N, 4 * (size_t)rows * N, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) return fail(e, "d2h E");
+    }
+  }
+  if ((e = cudaStreamSynchronize(s_out)) != cudaSuccess) return fail(e, "dgs_spmm_csr_host(sync out)");
+  if ((e = cudaStreamSynchronize(s_k)) != cudaSuccess) return fail(e, "dgs_spmm_csr_host(sync compute)");
+  return ok_or(cudaStreamSynchronize(s_in), "dgs_spmm_csr_host(sync in)");
 }
 
 int dgs_sddmm_csr_host(int M, int Kdim, int ncols, int64_t nnz, const int *rowptr, const int *col, const float *D1,

@@ -174,6 +174,31 @@ def test_host_buffer_entry(oracle, graphs):
     assert np.array_equal(C, ref) and np.array_equal(E, Eref)
 
 
+def test_host_buffer_entry_pipelined_row_blocks(oracle, graphs, monkeypatch):
+    """The host entry cuts the CSR into row blocks of ~equal nnz and overlaps H2D / SpMM / D2H: force many blocks
+    (skewed rows, empty rows at block boundaries) and require the same answer as the one-block path."""
+    import dgsparse._lib as L
+    rowptr, col = graphs.reddit_like(1 / 32)
+    M = rowptr.size - 1
+    N = 64
+    val = graphs.uniform(col.size, 1, 0.5, 1.5)
+    B = graphs.uniform(M * N, 2, -1, 1).reshape(M, N)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    outs = []
+    for blk in (str(1 << 40), str(max(1000, col.size // 11))):
+        monkeypatch.setenv("DGS_HOST_BLOCK_NNZ", blk)
+        C = np.full((M, N), np.nan, np.float32)
+        E = np.full((M, N), -7, np.int32)
+        L.check(L.lib.dgs_spmm_csr_host(M, M, N, col.size, p(rowptr), p(col), p(val), p(B), p(C), p(E), 1, 2), "host max")
+        Cs = np.full((M, N), np.nan, np.float32)
+        L.check(L.lib.dgs_spmm_csr_host(M, M, N, col.size, p(rowptr), p(col), p(val), p(B), p(Cs), None, 0, 2), "host sum")
+        outs.append((C, E, Cs))
+    ref, Eref = oracle.spmm(rowptr, col, val, B, "max", with_arg=True)
+    for C, E, Cs in outs:
+        assert np.array_equal(C, ref) and np.array_equal(E, Eref)
+        assert_close_f32(Cs, oracle.spmm(rowptr, col, val, B), oracle.spmm_f64(rowptr, col, val, B), what="host sum blocks")
+
+
 def test_reddit_like_scaled_parity(K, oracle, graphs):
     """Same generator as the bench workload (config 2) at 1/16 scale: hub rows of thousands of nnz."""
     rowptr, col = graphs.reddit_like(1 / 16)
