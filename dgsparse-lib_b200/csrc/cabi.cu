@@ -177,8 +177,8 @@ int dgs_edge_softmax(int M, int head, const int *rowptr, const float *values, fl
 }
 
 // ---- sparse convolution ---------------------------------------------------------------------------
-size_t dgs_spconv_workspace_bytes(int k_vol, int c_in, int c_out, int precision) {
-  return dgs::spconv_workspace_bytes(k_vol, c_in, c_out, precision);
+size_t dgs_spconv_workspace_bytes(int rows, int k_vol, int c_in, int c_out, int precision) {
+  return dgs::spconv_workspace_bytes(rows, k_vol, c_in, c_out, precision);
 }
 
 int dgs_spconv_fwd(int in_nnz, int out_nnz, int k_vol, int c_in, int c_out, const int *kpos, const int *qkpos,

@@ -24,6 +24,7 @@
 // output, `separate_mid` runs the centre offset as identity-mapped tiles of the same kernel instead of a cuBLAS call.
 #include <cuda_bf16.h>
 #include <cstdint>
+#include <cstdlib>
 #include "common.cuh"
 #include "spmm.h"
 #include "spconv.h"
@@ -51,6 +52,11 @@ struct SpconvArgs {
   int n_id_tiles;             // identity-mapped tiles of the centre offset (separate_mid)
   int id_rows, mid_k;         // rows covered by the identity tiles, centre offset index
   int tiles_per_cta;
+  // pipelined kernel: gather source in the MMA dtype (fp32 input itself for tf32, a bf16 copy for bf16)
+  const uint8_t *feat;
+  int64_t feat_pitch;        // bytes between rows
+  int feat_valid_bytes;      // bytes of a row that hold channels (the rest of the last atom is zero-filled)
+  int n_stages;              // shared-memory A stages
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -289,6 +295,261 @@ __global__ void __launch_bounds__(128) spconv_fgms_tc_kernel(const SpconvArgs a)
   if (warp == 0) tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
 }
 
+// ---- the pipelined (warp-specialised, persistent) tile kernel -----------------------------------------------------------
+// Same math as spconv_fgms_tc_kernel, organised as three concurrent roles per CTA (one CTA per SM, a contiguous run of
+// tiles each) so that the gather of tile i+2, the MMA of tile i+1 and the scatter of tile i overlap:
+//   warps 0-3  gather   cp.async (LDGSTS) 16 B per lane straight into the swizzled K-major stage ring — no data
+//                       registers, DEPTH tiles in flight per thread; rows beyond the pair list / channels beyond c_in
+//                       are zero-filled by cp.async's src-size operand.  For tf32 the fp32 input is copied verbatim
+//                       (the tensor core reads the top 19 bits); for bf16 the features are converted once per call.
+//                       After wait_group: fence.proxy.async, then arrive on full[stage].
+//   warp 8     MMA      one lane: wait full[stage] and tmem_empty[buf], issue the tcgen05.mma chain into one of two
+//                       TMEM accumulators, commit to empty[stage] (stage reusable) and tmem_full[buf].
+//   warps 4-7  scatter  wait tmem_full[buf], tcgen05.ld the 32 rows of their TMEM lane quadrant, red.global.add.v4
+//                       into out[omap[p], :], arrive on tmem_empty[buf].
+// W[k]^T stays resident in shared memory; when the kernel offset changes inside a CTA's run the gather warps drain the
+// outstanding MMAs (wait on the empty barriers) and reload it.
+constexpr int kPipeThreads = 288;
+constexpr int kPipeMaxStages = 4;
+constexpr int kStgCols = 32;   // accumulator columns staged per pass of the scatter
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+// Walks consecutive tiles: kernel offset k and the pair range of each tile.  One binary search at the first tile, then
+// k only moves forward (a couple of dependent loads per offset change instead of a search per tile).
+struct TileCursor {
+  int k, q_lo, q_hi, kp, kpe;   // qkpos[k], qkpos[k+1], kpos[k], kpos[k+1]
+  int pbase, pend;
+  bool identity;
+  __device__ __forceinline__ void init(const SpconvArgs &a, int tile) {
+    if (tile < a.n_map_tiles) {
+      k = upper_bound_i32(a.qkpos, a.k_vol + 1, tile * kTileM) - 1;
+      q_lo = __ldg(a.qkpos + k); q_hi = __ldg(a.qkpos + k + 1);
+      kp = __ldg(a.kpos + k); kpe = __ldg(a.kpos + k + 1);
+    } else {
+      k = a.k_vol; q_lo = q_hi = kp = kpe = 0;
+    }
+  }
+  __device__ __forceinline__ void seek(const SpconvArgs &a, int tile) {   // tile must not decrease between calls
+    if (tile < a.n_map_tiles) {
+      const int q0 = tile * kTileM;
+      while (q0 >= q_hi) {
+        k++;
+        q_lo = q_hi; q_hi = __ldg(a.qkpos + k + 1);
+        kp = kpe; kpe = __ldg(a.kpos + k + 1);
+      }
+      pbase = q0 - q_lo + kp; pend = kpe; identity = false;
+    } else {
+      pbase = (tile - a.n_map_tiles) * kTileM; pend = a.id_rows; identity = true;
+    }
+  }
+  __device__ __forceinline__ int offset(const SpconvArgs &a) const { return identity ? a.mid_k : k; }
+};
+
+template <int KIND, int DEPTH>
+__global__ void __launch_bounds__(kPipeThreads, 1) spconv_fgms_pipe_kernel(const SpconvArgs a) {
+  using KD = Kind<KIND>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_full[kPipeMaxStages], s_empty[kPipeMaxStages], s_tfull[2], s_tempty[2];
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.n_stages;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = (uint32_t)a.n_atoms * kTileM * kAtomBytes;
+  const uint32_t sW = base + (uint32_t)S * stage_bytes;   // [n_atoms][NT rows][128 B]
+  const uint32_t sStage = sW + (uint32_t)a.n_atoms * a.NT * kAtomBytes;   // [4 warps][32 rows][32 + 4] fp32 scatter staging
+  const int n0 = blockIdx.y * a.NT;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) { mbar_init(&s_full[s], 128); mbar_init(&s_empty[s], 1); }
+    for (int t = 0; t < 2; t++) { mbar_init(&s_tfull[t], 1); mbar_init(&s_tempty[t], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(&s_tmem, (uint32_t)(2 * a.tmem_cols));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  const int n_tiles = a.n_map_tiles + a.n_id_tiles;
+  const int t_begin = blockIdx.x * a.tiles_per_cta;
+  const int n_my = max(0, min(n_tiles, t_begin + a.tiles_per_cta) - t_begin);
+
+  if (warp < 4) {
+    // ================= gather =================
+    const int cpr = a.n_atoms * 8;                 // 16-byte chunks per row
+    int resident_k = -1;
+    int na = 0;   // next tile whose full[] arrival this thread still owes (its copies may still be in flight)
+    TileCursor cur;
+    int next_in = -1;   // imap entry of this lane's row of the NEXT tile, loaded one tile ahead
+    if (n_my > 0) {
+      cur.init(a, t_begin);
+      cur.seek(a, t_begin);
+      const int p = cur.pbase + warp * 32 + lane;
+      if (p < cur.pend) next_in = cur.identity ? p : __ldg(a.imap + p);
+    }
+    for (int i = 0; i < n_my; i++) {
+      const int s = i % S;
+      const int my_in = next_in;                   // row 32*warp + lane of this tile gathers input row my_in
+      const int tile_k = cur.offset(a);
+      if (i + 1 < n_my) {                          // prefetch the map entry of the next tile behind this tile's copies
+        cur.seek(a, t_begin + i + 1);
+        const int p = cur.pbase + warp * 32 + lane;
+        next_in = -1;
+        if (p < cur.pend) next_in = cur.identity ? p : __ldg(a.imap + p);
+      }
+      if (tile_k != resident_k) {
+        // The resident W changes: hand over every tile gathered so far, wait until all their MMAs have completed
+        // (they read the resident W), then load W[k]^T rows [n0, n0 + NT).
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        fence_proxy_async_smem();
+        for (; na < i; na++) mbar_arrive(&s_full[na % S]);
+        for (int j = max(0, i - S); j < i; j++) mbar_wait(&s_empty[j % S], (uint32_t)(j / S) & 1u);
+        const int k_pad_bytes = a.n_atoms * kAtomBytes;
+        const uint8_t *wk = a.Wt + ((size_t)tile_k * a.n_rows_pad + n0) * k_pad_bytes;
+        const int items = a.NT * cpr;
+        for (int idx = tid; idx < items; idx += 128) {
+          const int c = idx & 7, at = (idx >> 3) % a.n_atoms, n = idx / cpr;
+          const uint4 w = __ldg(reinterpret_cast<const uint4 *>(wk + (size_t)n * k_pad_bytes + at * kAtomBytes + c * 16));
+          const uint32_t dst = sW + (uint32_t)at * (a.NT * kAtomBytes) + (uint32_t)n * kAtomBytes + (uint32_t)((c ^ (n & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+        }
+        resident_k = tile_k;
+      } else if (i >= S) {
+        mbar_wait(&s_empty[s], (uint32_t)(i / S - 1) & 1u);   // the MMA that read this stage (tile i - S) is done
+      }
+      const uint32_t sA = base + (uint32_t)s * stage_bytes;
+      // this warp's 32 rows x cpr chunks, consecutive lanes on consecutive chunks of a row (coalesced 16 B each)
+      int rl = lane / cpr, cc = lane % cpr;
+      const int drl = 32 / cpr, dcc = 32 % cpr;
+      for (int it = 0; it < cpr; it++) {
+        const int in_row = __shfl_sync(0xffffffffu, my_in, rl);
+        const int r = warp * 32 + rl, at = cc >> 3, c = cc & 7;
+        const bool ok = in_row >= 0 && cc * 16 < a.feat_valid_bytes;
+        const uint32_t dst = sA + (uint32_t)at * (kTileM * kAtomBytes) + (uint32_t)r * kAtomBytes + (uint32_t)((c ^ (r & 7)) << 4);
+        cp_async16_zfill(dst, ok ? a.feat + (size_t)in_row * a.feat_pitch + cc * 16 : a.feat, ok ? 16u : 0u);
+        rl += drl; cc += dcc;
+        if (cc >= cpr) { cc -= cpr; rl += 1; }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (i - na >= DEPTH) {   // the oldest owed tile has at most DEPTH younger groups behind it: wait for it only
+        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH) : "memory");
+        fence_proxy_async_smem();
+        mbar_arrive(&s_full[na % S]);
+        na++;
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    fence_proxy_async_smem();
+    for (; na < n_my; na++) mbar_arrive(&s_full[na % S]);
+  } else if (warp == 8) {
+    // ================= MMA issue =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc<KIND>(a.NT);
+      for (int i = 0; i < n_my; i++) {
+        const int s = i % S, t = i & 1;
+        mbar_wait(&s_full[s], (uint32_t)(i / S) & 1u);
+        if (i >= 2) mbar_wait(&s_tempty[t], (uint32_t)(i / 2 - 1) & 1u);
+        tc_fence_after();
+        const uint32_t sA = base + (uint32_t)s * stage_bytes;
+        const uint32_t d_tmem = tmem + (uint32_t)(t * a.tmem_cols);
+        for (int at = 0; at < a.n_atoms; at++) {
+          const int ch0 = at * KD::kElemsPerAtom;
+          const int ksteps = (min(KD::kElemsPerAtom, a.c_in - ch0) + KD::kUmmaK - 1) / KD::kUmmaK;
+          for (int ks = 0; ks < ksteps; ks++) {
+            const uint64_t ad = umma_desc_k128(sA + (uint32_t)at * (kTileM * kAtomBytes) + (uint32_t)ks * 32);
+            const uint64_t bd = umma_desc_k128(sW + (uint32_t)at * (a.NT * kAtomBytes) + (uint32_t)ks * 32);
+            umma<KIND>(d_tmem, ad, bd, idesc, (at + ks) > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&s_empty[s]);
+        umma_commit(&s_tfull[t]);
+      }
+    }
+  } else {
+    // ================= scatter =================
+    const int q = warp - 4;   // == warp % 4: the TMEM lane quadrant this warp may read
+    constexpr int pitch = kStgCols + 4;           // floats per staged row (+16 B: conflict-free 128-bit rows)
+    float *stg = reinterpret_cast<float *>(smem_raw + (sStage - smem_u32(smem_raw))) + (size_t)q * 32 * pitch;
+    TileCursor cur;
+    int next_out = -1;        // omap entry of this lane's row of the NEXT tile, loaded one tile ahead
+    if (n_my > 0) {
+      cur.init(a, t_begin);
+      cur.seek(a, t_begin);
+      const int p = cur.pbase + q * 32 + lane;
+      if (p < cur.pend) next_out = cur.identity ? p : __ldg(a.omap + p);
+    }
+    for (int i = 0; i < n_my; i++) {
+      const int t = i & 1;
+      const int out_row = next_out;
+      if (i + 1 < n_my) {
+        cur.seek(a, t_begin + i + 1);
+        const int p = cur.pbase + q * 32 + lane;
+        next_out = -1;
+        if (p < cur.pend) next_out = cur.identity ? p : __ldg(a.omap + p);
+      }
+      mbar_wait(&s_tfull[t], (uint32_t)(i / 2) & 1u);
+      tc_fence_after();
+      // TMEM -> registers (thread = row) -> this warp's staging tile in shared memory, so that the scatter below
+      // issues whole contiguous row segments per instruction (full 32 B sectors at the L2 atomic units instead of
+      // 32 lanes x 16 B of 32 different rows)
+      const uint32_t taddr = tmem + (uint32_t)(t * a.tmem_cols) + ((uint32_t)(q * 32) << 16);
+      for (int cb = 0; cb < a.NT; cb += kStgCols) {   // column blocks of <= 32: bounds the staging tile
+        const int cw = min(kStgCols, a.NT - cb), cpn = cw / 4;
+        for (int c0 = 0; c0 < cw; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + (uint32_t)(cb + c0), v);
+          float4 *dst = reinterpret_cast<float4 *>(stg + (size_t)lane * pitch + c0);
+#pragma unroll
+          for (int j = 0; j < 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (cb + kStgCols >= a.NT) {   // accumulator fully read: the MMA warp may reuse this TMEM buffer
+          tc_fence_before();
+          mbar_arrive(&s_tempty[t]);
+        }
+        __syncwarp();
+        int rl = lane / cpn, cc = lane % cpn;
+        const int drl = 32 / cpn, dcc = 32 % cpn;
+        for (int it = 0; it < cpn; it++) {
+          const int orow = __shfl_sync(0xffffffffu, out_row, rl);
+          const int col = n0 + cb + cc * 4;
+          if (orow >= 0 && col < a.c_out) {
+            const float4 x = *reinterpret_cast<const float4 *>(stg + (size_t)rl * pitch + cc * 4);
+            red_add_v4(a.out + (int64_t)orow * a.ld_out + col, x.x, x.y, x.z, x.w);
+          }
+          rl += drl; cc += dcc;
+          if (cc >= cpn) { cc -= cpn; rl += 1; }
+        }
+        __syncwarp();              // staging tile free for the next block / accumulator
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, (uint32_t)(2 * a.tmem_cols));
+}
+
+// fp32 features -> bf16 rows of k_pad elements (zero padded), once per call, for the pipelined bf16 gather
+__global__ void __launch_bounds__(256) spconv_to_bf16_kernel(const float *__restrict__ in, int64_t ld_in, int rows, int c_in,
+                                                             int k_pad, __nv_bfloat16 *__restrict__ out) {
+  const int chunks = k_pad / 8;
+  const int64_t total = (int64_t)rows * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / chunks), ch = (int)(i % chunks) * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = ch + e < c_in ? __ldg(in + (int64_t)r * ld_in + ch + e) : 0.0f;
+    uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4 *>(out + (int64_t)r * k_pad + ch) = o;
+  }
+}
+
 // ---- W preparation: Wt[k][n][c] = W[k][c * sc + n * sn] converted to the MMA dtype, zero padded -----------------------
 template <int KIND>
 __global__ void __launch_bounds__(256) spconv_prep_weights_kernel(const float *__restrict__ W, uint8_t *__restrict__ Wt, int k_vol,
@@ -477,12 +738,15 @@ TcGeometry tc_geometry(int kdim, int ndim, int precision) {
 
 }  // namespace
 
-size_t spconv_workspace_bytes(int k_vol, int c_in, int c_out, int precision) {
+size_t spconv_workspace_bytes(int rows, int k_vol, int c_in, int c_out, int precision) {
   if (precision == SPCONV_FP32) return 256;
-  // large enough for the forward (K = c_in, N = c_out) and the dX backward (K = c_out, N = c_in)
+  // large enough for the forward (K = c_in, N = c_out) and the dX backward (K = c_out, N = c_in):
+  // the prepared weights, plus (bf16) a converted copy of the gathered feature matrix of `rows` rows
   const TcGeometry f = tc_geometry(c_in, c_out, precision), b = tc_geometry(c_out, c_in, precision);
   const size_t wf = (size_t)k_vol * f.n_rows_pad * f.k_pad * f.esize, wb = (size_t)k_vol * b.n_rows_pad * b.k_pad * b.esize;
-  return (wf > wb ? wf : wb) + 256;
+  size_t need = (wf > wb ? wf : wb) + 512;
+  if (precision == SPCONV_BF16) need += (size_t)(rows > 0 ? rows : 0) * (f.k_pad > b.k_pad ? f.k_pad : b.k_pad) * 2 + 256;
+  return need;
 }
 
 cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -533,6 +797,50 @@ cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspac
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
   a.Wt = Wt; a.n_atoms = g.n_atoms; a.n_rows_pad = g.n_rows_pad; a.NT = g.NT; a.tmem_cols = g.tmem_cols;
+  a.feat = nullptr; a.feat_pitch = 0; a.feat_valid_bytes = 0; a.n_stages = 0;
+
+  // pipelined kernel when at least two whole-K stages and the W panel fit in shared memory
+  {
+    const size_t stage_bytes = (size_t)g.n_atoms * kTileM * kAtomBytes, w_smem = (size_t)g.n_atoms * g.NT * kAtomBytes;
+    const size_t stg_smem = (size_t)4 * 32 * (kStgCols + 4) * 4;   // scatter staging of the four epilogue warps
+    const size_t budget = 225u * 1024u;
+    int S = w_smem + stg_smem < budget ? (int)((budget - w_smem - stg_smem) / stage_bytes) : 0;
+    if (S > kPipeMaxStages) S = kPipeMaxStages;
+    bool pipe = S >= 2 && !getenv("DGS_SPCONV_NO_PIPE");
+    if (pipe && p.precision == SPCONV_BF16) {   // converted feature copy lives behind the weights in the workspace
+      uint8_t *feat = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(Wt + w_bytes) + 255) & ~(uintptr_t)255);
+      const size_t f_bytes = (size_t)p.in_rows * g.k_pad * 2;
+      if (feat + f_bytes > reinterpret_cast<uint8_t *>(workspace) + workspace_bytes) {
+        pipe = false;
+      } else if (p.in_rows > 0) {
+        const int64_t chunks = (int64_t)p.in_rows * (g.k_pad / 8);
+        const int cb = (int)((chunks + 255) / 256 < 8192 ? (chunks + 255) / 256 : 8192);
+        spconv_to_bf16_kernel<<<cb, 256, 0, stream>>>(p.in, p.ld_in, p.in_rows, p.kdim, g.k_pad, reinterpret_cast<__nv_bfloat16 *>(feat));
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        a.feat = feat; a.feat_pitch = (int64_t)g.k_pad * 2; a.feat_valid_bytes = g.k_pad * 2;
+      }
+    } else if (pipe) {
+      a.feat = reinterpret_cast<const uint8_t *>(p.in); a.feat_pitch = p.ld_in * 4; a.feat_valid_bytes = p.kdim * 4;
+    }
+    if (pipe && a.feat != nullptr) {
+      a.n_stages = S;
+      int ctas = device_sm_count() / g.grid_y;
+      if (ctas < 1) ctas = 1;
+      a.tiles_per_cta = (n_tiles + ctas - 1) / ctas;
+      dim3 grid((n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta, g.grid_y);
+      const size_t smem = 1024 + (size_t)S * stage_bytes + w_smem + stg_smem;
+#define DGS_PIPE(KIND_, DEPTH_)                                                                                             \
+  do {                                                                                                                      \
+    if ((e = cudaFuncSetAttribute(spconv_fgms_pipe_kernel<KIND_, DEPTH_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                  (int)smem)) != cudaSuccess) return e;                                                     \
+    spconv_fgms_pipe_kernel<KIND_, DEPTH_><<<grid, kPipeThreads, smem, stream>>>(a);                                        \
+  } while (0)
+      if (p.precision == SPCONV_TF32) { if (S >= 3) DGS_PIPE(0, 2); else DGS_PIPE(0, 1); }
+      else { if (S >= 3) DGS_PIPE(1, 2); else DGS_PIPE(1, 1); }
+#undef DGS_PIPE
+      return cudaGetLastError();
+    }
+  }
   // a run of tiles per CTA amortises the W[k] panel; keep >= ~8 CTAs per SM in flight for latency hiding
   const int sms = device_sm_count();
   int tpc = n_tiles / (sms * 8);

@@ -31,7 +31,7 @@ struct SpconvProblem {
   int accumulate = 0;           // 0: out is zeroed first
 };
 
-size_t spconv_workspace_bytes(int k_vol, int c_in, int c_out, int precision);
+size_t spconv_workspace_bytes(int rows, int k_vol, int c_in, int c_out, int precision);   // rows = max(in_nnz, out_nnz)
 cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // dW[k] = sum_p in[imap[p], :]^T (x) dout[omap[p], :]   (kernel gradient), fp32 accumulate

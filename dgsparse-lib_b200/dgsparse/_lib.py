@@ -32,7 +32,7 @@ SIGNATURES = {
     "dgs_csr2csc_workspace_bytes": (_sz, [_i32, _i32, _i64]),
     "dgs_csr2csc": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgs_edge_softmax": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp]),
-    "dgs_spconv_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "dgs_spconv_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "dgs_spconv_fwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
     "dgs_spconv_bwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                               _vp, _sz, _vp]),

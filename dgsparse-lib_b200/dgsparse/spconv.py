@@ -81,7 +81,7 @@ def spconv_fwd_fused(in_feats, kernel, kpos, qkpos, in_map, out_map, out_nnz, su
     k_vol, c_in, c_out = w.shape
     with torch.cuda.device(x.device):
         out = torch.empty((out_nnz, c_out), dtype=torch.float32, device=x.device)
-        ws = _workspace(lib.dgs_spconv_workspace_bytes(k_vol, c_in, c_out, prec), x.device)
+        ws = _workspace(lib.dgs_spconv_workspace_bytes(max(x.size(0), out_nnz), k_vol, c_in, c_out, prec), x.device)
         check(lib.dgs_spconv_fwd(x.size(0), out_nnz, k_vol, c_in, c_out, ptr(kpos), ptr(qkpos), ptr(in_map), ptr(out_map),
                                  int(sum_nnz), ptr(x), ptr(w), ptr(out), int(bool(separate_mid)), prec, ptr(ws),
                                  ws.numel(), stream_of(x)), "dgs_spconv_fwd")
@@ -100,7 +100,7 @@ def spconv_bwd_fused(out_feats_grad, in_feats, kernel, kpos, qkpos, in_map, out_
     with torch.cuda.device(x.device):
         gin = torch.empty_like(x) if need_in else None
         gk = torch.empty_like(w) if need_kernel else None
-        ws = _workspace(lib.dgs_spconv_workspace_bytes(k_vol, c_in, c_out, prec), x.device)
+        ws = _workspace(lib.dgs_spconv_workspace_bytes(max(x.size(0), g.size(0)), k_vol, c_in, c_out, prec), x.device)
         check(lib.dgs_spconv_bwd(x.size(0), g.size(0), k_vol, c_in, c_out, ptr(kpos), ptr(qkpos), ptr(in_map),
                                  ptr(out_map), int(sum_nnz), ptr(g), ptr(x), ptr(w), ptr(gin), ptr(gk),
                                  int(bool(separate_mid)), prec, ptr(ws), ws.numel(), stream_of(x)), "dgs_spconv_bwd")
