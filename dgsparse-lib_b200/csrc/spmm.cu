@@ -12,11 +12,11 @@ namespace dgs {
 DGS_DECL_LOOKUP(4, 4) DGS_DECL_LOOKUP(4, 8) DGS_DECL_LOOKUP(4, 16) DGS_DECL_LOOKUP(4, 32)
 DGS_DECL_LOOKUP(1, 4) DGS_DECL_LOOKUP(1, 8) DGS_DECL_LOOKUP(1, 16) DGS_DECL_LOOKUP(1, 32)
 
-template <bool ARG> static cudaError_t launch_fixup(int red, const SpmmArgs &a, int blocks, cudaStream_t s) {
+template <bool ARG, int FV> static cudaError_t launch_fixup(int red, const SpmmArgs &a, int blocks, cudaStream_t s) {
   switch (red) {
-  case R_MAX: spmm_fixup_kernel<R_MAX, ARG><<<blocks, 256, 0, s>>>(a); break;
-  case R_MIN: spmm_fixup_kernel<R_MIN, ARG><<<blocks, 256, 0, s>>>(a); break;
-  default: spmm_fixup_kernel<R_SUM, false><<<blocks, 256, 0, s>>>(a); break;
+  case R_MAX: spmm_fixup_kernel<R_MAX, ARG, FV><<<blocks, 256, 0, s>>>(a); break;
+  case R_MIN: spmm_fixup_kernel<R_MIN, ARG, FV><<<blocks, 256, 0, s>>>(a); break;
+  default: spmm_fixup_kernel<R_SUM, false, FV><<<blocks, 256, 0, s>>>(a); break;
   }
   return cudaGetLastError();
 }
@@ -192,12 +192,15 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
     }
     if (e != cudaSuccess) return e;
   }
-  const int64_t fold_threads = (int64_t)a.num_chunks * p.N;
+  const int fv = can_vec4 ? 4 : 1;
+  const int64_t fold_threads = (int64_t)a.num_chunks * (p.N / fv);
   const int64_t empty_threads = ((int64_t)p.M + 31) / 32 * 32;
   const int64_t threads = fold_threads > empty_threads ? fold_threads : empty_threads;
   const int blocks = (int)((threads + 255) / 256);
   ProfileScope prof(2, stream);
-  return with_arg ? launch_fixup<true>(p.reduce, a, blocks, stream) : launch_fixup<false>(p.reduce, a, blocks, stream);
+  if (can_vec4)
+    return with_arg ? launch_fixup<true, 4>(p.reduce, a, blocks, stream) : launch_fixup<false, 4>(p.reduce, a, blocks, stream);
+  return with_arg ? launch_fixup<true, 1>(p.reduce, a, blocks, stream) : launch_fixup<false, 1>(p.reduce, a, blocks, stream);
 }
 
 }  // namespace dgs

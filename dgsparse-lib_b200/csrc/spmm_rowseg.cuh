@@ -249,34 +249,50 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
 
 // Folds the partials of rows cut by segment boundaries (one thread per (segment, column)), in segment
 // order, and writes empty rows (0 and E = -1: include/cuda/spmm_cuda.cuh:49-53, src/gspmm-fp/gspmm.cu:222).
-template <int RED, bool ARG>
+// FV = 4: one thread folds four adjacent columns (16-byte loads of the partials, 16-byte stores to every
+// destination — with NVLink peers as destinations the store count is what matters); FV = 1: any N / alignment.
+template <int RED, bool ARG, int FV>
 __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t n_fold = (int64_t)a.num_chunks * a.N;
+  const int nq = a.N / FV;                      // column groups per row
+  const int64_t n_fold = (int64_t)a.num_chunks * nq;
   if (t < n_fold) {
-    const int g = (int)(t / a.N);
-    const int c = (int)(t % a.N);
+    const int g = (int)(t / nq);
+    const int c = (int)(t % nq) * FV;
     const int r = a.tail_row[g];
     if (r >= 0) {
       const int start = __ldg(a.rowptr + r), end = __ldg(a.rowptr + r + 1);
       const int g_last = (end - 1) / a.chunk;
-      float acc = a.part_val[((size_t)g * 2 + 1) * a.N + c];
-      int arg = ARG ? a.part_arg[((size_t)g * 2 + 1) * a.N + c] : -1;
+      float acc[FV];
+      int arg[FV];
+      ld_vec<FV>(acc, a.part_val + ((size_t)g * 2 + 1) * a.N + c);
+      if (ARG) ld_ivec<FV>(arg, a.part_arg + ((size_t)g * 2 + 1) * a.N + c);
       for (int gg = g + 1; gg <= g_last; gg++) {
-        const float x = a.part_val[((size_t)gg * 2) * a.N + c];
-        if (RED == R_MAX) {
-          if (ARG) { if (acc < x) arg = a.part_arg[((size_t)gg * 2) * a.N + c]; }
-          acc = (acc < x) ? x : acc;
-        } else if (RED == R_MIN) {
-          if (ARG) { if (acc > x) arg = a.part_arg[((size_t)gg * 2) * a.N + c]; }
-          acc = (acc < x) ? acc : x;
-        } else {
-          acc += x;
+        float x[FV];
+        int xa[FV];
+        ld_vec<FV>(x, a.part_val + ((size_t)gg * 2) * a.N + c);
+        if (ARG) ld_ivec<FV>(xa, a.part_arg + ((size_t)gg * 2) * a.N + c);
+#pragma unroll
+        for (int v = 0; v < FV; v++) {
+          if (RED == R_MAX) {
+            if (ARG) { if (acc[v] < x[v]) arg[v] = xa[v]; }
+            acc[v] = (acc[v] < x[v]) ? x[v] : acc[v];
+          } else if (RED == R_MIN) {
+            if (ARG) { if (acc[v] > x[v]) arg[v] = xa[v]; }
+            acc[v] = (acc[v] < x[v]) ? acc[v] : x[v];
+          } else {
+            acc[v] += x[v];
+          }
         }
       }
-      if (a.mean) acc = acc / (float)(end - start);
-      for (int d = 0; d < a.n_dst; d++) a.dst[d][(size_t)r * a.ldc + c] = acc;
-      if (ARG) a.E[(size_t)r * a.lde + c] = arg;
+      if (a.mean) {
+        const float deg = (float)(end - start);
+#pragma unroll
+        for (int v = 0; v < FV; v++) acc[v] = acc[v] / deg;
+      }
+      const size_t off = (size_t)r * a.ldc + c;
+      for (int d = 0; d < a.n_dst; d++) st_vec_cs<FV>(a.dst[d] + off, acc);
+      if (ARG) st_vec_cs<FV>(a.E + (size_t)r * a.lde + c, arg);
     }
   }
   // empty rows: one warp scans 32 rows, then writes the zero rows cooperatively
