@@ -396,7 +396,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak,
                          "traffic": ncu_traffic(args.workload) if args.scale == 1.0 else None, "peak_source": peak_src,
-                         "kernel": "spmm_rowseg_kernel" if main_id == 1 else "sddmm_kernel",
+                         "kernel": "spmm_rowseg_kernel" if main_id == 1 else "sddmm_ring_kernel",
                          "kernel_ms_avg": k_avg, "fixup_ms_avg": (sum(fix_ms) / len(fix_ms)) if fix_ms else None,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "gather_bytes_per_launch": 4.0 * nnz * N,

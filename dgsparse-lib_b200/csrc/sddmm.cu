@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kSdThreads) sddmm_kernel(const SddmmArgs a) {
 }
 
 
-// ---- shared-memory ring variant (rows of 512 B .. 4 KB) ---------------------------------------------------------------
+// ---- shared-memory ring variant (rows of 256 B .. 4 KB) ---------------------------------------------------------------
 // A random 1 KB-row gather is latency bound: the register-staged kernel above holds its loads in 112 registers, sits
 // at 20 % warp occupancy and leaves every warp on long-scoreboard.  Here the operand rows go global -> shared with
 // cp.async (LDGSTS, 16 B per lane, no data registers): a warp keeps STAGES-1 batches of NB edges (NB D2 rows + the
@@ -420,8 +420,8 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
   auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   const bool vec4 = (p.K % 4 == 0) && (p.ld1 % 4 == 0) && (p.ld2 % 4 == 0) && al16(p.D1) && al16(p.D2) &&
                     (!mask || al16(p.E));
-  // rows of 512 B .. 4 KB made of aligned 16-byte chunks: shared-memory ring kernel
-  if (vec4 && !mask && p.K >= 128 && p.K <= 1024 && !getenv("DGS_SDDMM_NO_RING")) {
+  // rows of 256 B .. 4 KB made of aligned 16-byte chunks: shared-memory ring kernel
+  if (vec4 && !mask && p.K >= 64 && p.K <= 1024 && !getenv("DGS_SDDMM_NO_RING")) {
     SddmmRingArgs g;
     SddmmArgs &a = g.a;
     a.M = p.M; a.K = p.K; a.nnz = (int)p.nnz;
