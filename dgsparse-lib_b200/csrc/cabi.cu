@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "spmm.h"
 #include "spconv.h"
+#include "kmap.h"
 
 namespace {
 
@@ -78,6 +79,18 @@ __global__ void __launch_bounds__(256) spmm_colmajor_kernel(int M, int N, int K,
   const int end = __ldg(rowptr + r + 1);
   for (int p = __ldg(rowptr + r); p < end; p++) acc += (val ? __ldg(val + p) : 1.0f) * __ldg(Bn + __ldg(col + p));
   C[(size_t)n * M + r] = acc;
+}
+
+// rowptr[r] = first position p with rowIdx[p] >= r (rowIdx ascending): one binary search per row
+__global__ void __launch_bounds__(256) coo_to_rowptr_kernel(const int *__restrict__ rowIdx, int nnz, int nr, int *__restrict__ rowptr) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > nr) return;
+  int lo = 0, hi = nnz;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(rowIdx + mid) < r) lo = mid + 1; else hi = mid;
+  }
+  rowptr[r] = lo;
 }
 
 // ---- edge softmax --------------------------------------------------------------------------------
@@ -215,6 +228,22 @@ int dgs_spconv_bwd(int in_nnz, int out_nnz, int k_vol, int c_in, int c_out, cons
     if (rc) return rc;
   }
   return 0;
+}
+
+// ---- kernel maps ------------------------------------------------------------------------------------
+size_t dgs_kmap_workspace_bytes(int in_nnz, int out_nnz, int k_vol) { return dgs::kmap_workspace_bytes(in_nnz, out_nnz, k_vol); }
+
+int dgs_kmap_downsample(int in_nnz, const int *in_coords, int sx, int sy, int sz, int *out_coords, int *out_nnz_dev,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+  return ok_or(dgs::kmap_downsample(in_nnz, in_coords, sx, sy, sz, out_coords, out_nnz_dev, workspace, workspace_bytes,
+                                    (cudaStream_t)stream), "dgs_kmap_downsample");
+}
+
+int dgs_kmap_build(int in_nnz, const int *in_coords, int out_nnz, const int *out_coords, int ksx, int ksy, int ksz,
+                   int sx, int sy, int sz, int q, int skip_mid, int *imap, int *omap, int *knnz, int *kpos, int *qkpos,
+                   void *workspace, size_t workspace_bytes, void *stream) {
+  return ok_or(dgs::kmap_build(in_nnz, in_coords, out_nnz, out_coords, ksx, ksy, ksz, sx, sy, sz, q, skip_mid, imap, omap,
+                               knnz, kpos, qkpos, workspace, workspace_bytes, (cudaStream_t)stream), "dgs_kmap_build");
 }
 
 // ---- host-buffer entry points --------------------------------------------------------------------
@@ -421,6 +450,33 @@ void gespmmCsrSpMM(const SpMatCsrDescr_t A, float *B, const int N, float *C, boo
   if (e != cudaSuccess) { legacy_report(fail(e, "gespmmCsrSpMM(scratch)"), "gespmmCsrSpMM"); return; }
   legacy_report(dgs_spmm_csr(A.nrow, N, nnz, A.indptr, A.indices, A.data, B, N, C, N, nullptr, 0, DGS_SUM, DGS_MUL, ws,
                              need, nullptr), "gespmmCsrSpMM");
+}
+
+// ---- the older SpMV/SpMM API (src/ge-spmm/gespmm_v2.h) ----------------------------------------------
+void cuda_csr_spmm(int algo_code, int layout_code, int nr, int nc, int nv, int nnz, int *csrRowPtr, int *csrCol,
+                   float *csrVal, float *vin, float *vout) {
+  (void)algo_code;
+  if (layout_code != 0 && layout_code != 1) { fprintf(stderr, "[dgsparse_b200] cuda_csr_spmm: wrong layout code %d\n", layout_code); return; }
+  SpMatCsrDescr_t A = {nr, nc, nnz, csrRowPtr, csrCol, csrVal};
+  gespmmCsrSpMM(A, vin, nv, vout, /*transpose_BC (row-major) =*/layout_code == 1, GESPMM_ALG_DEFAULT);
+}
+
+void cuda_csr_coo_spmm(SPMV_SPMM_ALG kAlg, DenseLayout layout, const int nr, const int nc, const int nnz, const int nv,
+                       const int *rowPtr, const int *rowIdx, const int *colIdx, const float *values,
+                       const float *dnInput, float *dnOutput) {
+  (void)kAlg;
+  int *rp = const_cast<int *>(rowPtr);
+  if (rp == nullptr) {   // COO only: rebuild the row pointer from the sorted row indices in the legacy scratch
+    if (rowIdx == nullptr) { legacy_report(fail(cudaErrorInvalidValue, "cuda_csr_coo_spmm(rowPtr and rowIdx NULL)"), "cuda_csr_coo_spmm"); return; }
+    void *ws = nullptr;
+    const size_t spmm_ws = dgs::spmm_workspace_bytes(nv, nnz, false);
+    cudaError_t e = legacy_scratch(spmm_ws + 4 * ((size_t)nr + 1) + 512, &ws);
+    if (e != cudaSuccess) { legacy_report(fail(e, "cuda_csr_coo_spmm(scratch)"), "cuda_csr_coo_spmm"); return; }
+    rp = reinterpret_cast<int *>(static_cast<char *>(ws) + ((spmm_ws + 255) / 256 * 256));
+    coo_to_rowptr_kernel<<<(nr + 1 + 255) / 256, 256, 0, 0>>>(rowIdx, nnz, nr, rp);
+  }
+  SpMatCsrDescr_t A = {nr, nc, nnz, rp, const_cast<int *>(colIdx), const_cast<float *>(values)};
+  gespmmCsrSpMM(A, const_cast<float *>(dnInput), nv, dnOutput, layout == DENSE_ROW_MAJOR, GESPMM_ALG_DEFAULT);
 }
 
 void spmm_cuda(int m, int k, int *rowptr, int *colind, float *values, float *dense, float *out) {

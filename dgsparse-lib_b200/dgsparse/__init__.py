@@ -11,7 +11,7 @@ from .spmm import spmm_max, spmm_mean, spmm_sum, spmm_min
 from .tensor import SparseTensor
 from .storage import Storage
 from .ftransform import csr2csc
-from . import gspmm, sddmm, spconv  # noqa: F401  (spconv registers torch.ops.dgsparse_spconv.spconv)
+from . import gspmm, sddmm, spconv, sparse_mapping  # noqa: F401  (spconv registers torch.ops.dgsparse_spconv.spconv)
 
 __version__ = "0.1+b200"
 

@@ -36,6 +36,10 @@ SIGNATURES = {
     "dgs_spconv_fwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
     "dgs_spconv_bwd": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                               _vp, _sz, _vp]),
+    "dgs_kmap_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "dgs_kmap_downsample": (_i32, [_i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "dgs_kmap_build": (_i32, [_i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+                              _vp, _sz, _vp]),
     "dgs_ipc_export": (_i32, [_vp, _vp, ctypes.POINTER(_i64)]),
     "dgs_ipc_open": (_i32, [_vp, ctypes.POINTER(_vp)]),
     "dgs_ipc_close": (_i32, [_vp]),
@@ -49,6 +53,9 @@ SIGNATURES = {
     "sddmm_cuda_coo": (None, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "sddmm_cuda_csr": (None, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "edge_softmax_cuda": (None, [_i32, _i32, _vp, _vp, _vp]),
+    # the older SpMV/SpMM API, src/ge-spmm/gespmm_v2.h
+    "cuda_csr_coo_spmm": (None, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cuda_csr_spmm": (None, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

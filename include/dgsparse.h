@@ -70,6 +70,33 @@ void gespmmCsrSpMM(const struct SpMatCsrDescr_t spmatA, float *B, const int N, f
                    enum gespmmAlg_t alg);
 #endif
 
+/* The older SpMV/SpMM API of the same library, src/ge-spmm/gespmm_v2.h:8-38 (exported by lib/dgsparse.so):
+ * dnOutput[nr, nv] = A[nr, nc] . dnInput[nc, nv] for CSR (rowPtr) or COO (rowIdx, sorted by row) inputs.
+ * Every algorithm value computes the same product and runs the one row-segment kernel; the output is
+ * OVERWRITTEN (the reference's COO / merge algorithms accumulate with atomicAdd into a caller-zeroed buffer,
+ * gespmm_csrcoo_v2.cu:94-214 — same result).  values may be NULL (treated as 1, __guard_load_default_one).
+ * Any nv works (the reference handles nv in {1, 2, 4, 8, 16, 32} only). */
+enum SPMV_SPMM_ALG { ALG_CSR_SCALAR, ALG_CSR_VECTOR, ALG_COO_SCALAR, ALG_COO_VECTOR };
+enum SparseFormat { SPARSE_FORMAT_CSR, SPARSE_FORMAT_COO };
+enum DenseLayout { DENSE_ROW_MAJOR, DENSE_COL_MAJOR };
+
+/* replaces cuda_csr_coo_spmm, src/ge-spmm/gespmm_csrcoo_v2.cu:606-790.  rowPtr may be NULL for the COO algorithms
+ * (it is then rebuilt from rowIdx); rowIdx is ignored when rowPtr is given. */
+#ifdef __cplusplus
+void cuda_csr_coo_spmm(SPMV_SPMM_ALG kAlg, DenseLayout layout, const int nr, const int nc, const int nnz, const int nv,
+                       const int *rowPtr, const int *rowIdx, const int *colIdx, const float *values,
+                       const float *dnInput, float *dnOutput);
+#else
+void cuda_csr_coo_spmm(enum SPMV_SPMM_ALG kAlg, enum DenseLayout layout, const int nr, const int nc, const int nnz,
+                       const int nv, const int *rowPtr, const int *rowIdx, const int *colIdx, const float *values,
+                       const float *dnInput, float *dnOutput);
+#endif
+
+/* replaces cuda_csr_spmm, src/ge-spmm/gespmm_v2.cu:569-760.  algo_code 0..3 (row-scalar, row-vector, merge-scalar,
+ * merge-vector) all compute the same product; layout_code 0 = column-major, 1 = row-major dense operands. */
+void cuda_csr_spmm(int algo_code, int layout_code, int nr, int nc, int nv, int nnz, int *csrRowPtr, int *csrCol,
+                   float *csrVal, float *vin, float *vout);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,24 @@ int dgs_spconv_bwd(int in_nnz, int out_nnz, int k_vol, int c_in, int c_out, cons
                    const float *kernel, float *in_grad, float *kernel_grad, int separate_mid, int precision,
                    void *workspace, size_t workspace_bytes, void *stream);
 
+/* Kernel-map construction for sparse convolution (the reference's unregistered sparse_mapping,
+ * src/cuda/sparse_mapping.cu:20-161): from integer coordinates (batch, x, y, z) int32 [n, 4] to the pair lists the
+ * spconv op consumes.  |x|, |y|, |z| < 32768, 0 <= batch < 65536.
+ *   dgs_kmap_downsample: out_coords = sorted unique of (batch, floor(x/sx), floor(y/sy), floor(z/sz)), capacity in_nnz
+ *                        rows; the count is written to the DEVICE int *out_nnz_dev (coordsDownsample + sort + unique).
+ *   dgs_kmap_build:      for every kernel tap k = (kx*ksy + ky)*ksz + kz and output o, the input at
+ *                        out + (tap - (ks-1)/2) (all strides 1, _queryhash_subm) or out*stride + tap (_queryhash_sp,
+ *                        padding 0) if it exists.  imap / omap (capacity ksx*ksy*ksz*out_nnz each) are grouped by k and
+ *                        ordered by o inside a group (deterministic); knnz[k_vol], kpos[k_vol+1] and qkpos[k_vol+1]
+ *                        (counts rounded up to q, 128 for dgs_spconv_*) are device arrays; kpos[k_vol] = pair count.
+ *                        skip_mid != 0 leaves the centre tap out (for spconv's separate_mid). */
+size_t dgs_kmap_workspace_bytes(int in_nnz, int out_nnz, int k_vol);
+int dgs_kmap_downsample(int in_nnz, const int *in_coords, int sx, int sy, int sz, int *out_coords, int *out_nnz_dev,
+                        void *workspace, size_t workspace_bytes, void *stream);
+int dgs_kmap_build(int in_nnz, const int *in_coords, int out_nnz, const int *out_coords, int ksx, int ksy, int ksz,
+                   int sx, int sy, int sz, int q, int skip_mid, int *imap, int *omap, int *knnz, int *kpos, int *qkpos,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
 /* Peer memory for the fused column-shard epilogue: export a device allocation to the other ranks of
  * the box (CUDA IPC), open theirs; the opened base + offset is passed in dst[] of dgs_spmm_csr_multi. */
 int dgs_ipc_export(const void *dptr, void *handle64, int64_t *offset);

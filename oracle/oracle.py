@@ -115,6 +115,11 @@ def ref_cuda_lib():
             L.sddmm_cuda_csr.restype = None
             L.sddmm_cuda_coo.argtypes = [ci, ci, vp, vp, vp, vp, vp]
             L.sddmm_cuda_coo.restype = None
+            # older API, src/ge-spmm/gespmm_v2.h:19-37
+            L.cuda_csr_coo_spmm.argtypes = [ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp]
+            L.cuda_csr_coo_spmm.restype = None
+            L.cuda_csr_spmm.argtypes = [ci, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp]
+            L.cuda_csr_spmm.restype = None
             _ref_cuda = L
         return _ref_cuda
 

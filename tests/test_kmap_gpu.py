@@ -1,0 +1,97 @@
+"""GPU: kernel-map construction (dgs_kmap_*) against a plain-Python / numpy restatement of the reference's query rules
+(_queryhash_subm / _queryhash_sp with padding 0, include/cuda/sparse_mapping.cuh:68-229; coordsDownsample + sort + unique,
+src/cuda/sparse_mapping.cu:68-97).  Integer work: every output must be bit-exact.  The reference has no test or fixture
+for this step (parity unpinned); the end-to-end check below runs the maps through spconv against a dense convolution."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def random_coords(rng, n, batch, extent):
+    c = np.stack([rng.integers(0, batch, n), rng.integers(0, extent, n), rng.integers(0, extent, n), rng.integers(0, extent, n)], 1)
+    return np.unique(c, axis=0).astype(np.int32)          # voxel coordinates are unique
+
+
+def ref_kernel_map(in_c, ks, st, skip_mid=False):
+    """Restatement with a dict: returns (out_coords, imap, omap, knnz)."""
+    table = {tuple(c): i for i, c in reversed(list(enumerate(in_c.tolist())))}
+    sub = st == (1, 1, 1)
+    if sub:
+        out_c = in_c
+    else:
+        d = in_c.copy()
+        d[:, 1] //= st[0]; d[:, 2] //= st[1]; d[:, 3] //= st[2]
+        out_c = np.unique(d, axis=0)                        # lexicographic (batch, x, y, z)
+    k_vol = ks[0] * ks[1] * ks[2]
+    mid = k_vol // 2 if k_vol % 2 == 1 else 0
+    imap, omap, knnz = [], [], []
+    for k in range(k_vol):
+        kx, ky, kz = k // (ks[2] * ks[1]), (k // ks[2]) % ks[1], k % ks[2]
+        cnt = 0
+        if not (skip_mid and k == mid):
+            for o, (b, x, y, z) in enumerate(out_c.tolist()):
+                if sub:
+                    key = (b, x + kx - (ks[0] - 1) // 2, y + ky - (ks[1] - 1) // 2, z + kz - (ks[2] - 1) // 2)
+                else:
+                    key = (b, x * st[0] + kx, y * st[1] + ky, z * st[2] + kz)
+                i = table.get(key)
+                if i is not None:
+                    imap.append(i); omap.append(o); cnt += 1
+        knnz.append(cnt)
+    return out_c, np.array(imap, np.int32), np.array(omap, np.int32), np.array(knnz, np.int32)
+
+
+@pytest.mark.parametrize("ks,st,skip_mid", [(3, 1, False), (3, 1, True), (2, 2, False), (3, 2, False), ((1, 3, 3), 1, False),
+                                            (5, 1, False)])
+def test_kernel_map_bit_exact(ks, st, skip_mid):
+    from dgsparse.sparse_mapping import build_kernel_map, _triple
+    rng = np.random.default_rng(3)
+    in_c = random_coords(rng, 6000, 2, 24)
+    km = build_kernel_map(torch.from_numpy(in_c).cuda(), ks, st, separate_mid=skip_mid)
+    out_c, imap, omap, knnz = ref_kernel_map(in_c, _triple(ks), _triple(st), skip_mid)
+    assert np.array_equal(km.out_coords.cpu().numpy(), out_c)
+    assert np.array_equal(km.knnz.cpu().numpy(), knnz)
+    kpos = np.concatenate([[0], np.cumsum(knnz)]).astype(np.int32)
+    assert np.array_equal(km.kpos.cpu().numpy(), kpos)
+    q = np.concatenate([[0], np.cumsum((knnz + 127) // 128 * 128)]).astype(np.int32)
+    assert np.array_equal(km.qkpos.cpu().numpy(), q) and km.sum_nnz == int(q[-1])
+    assert np.array_equal(km.in_map.cpu().numpy(), imap) and np.array_equal(km.out_map.cpu().numpy(), omap)
+
+
+def test_edge_cases():
+    from dgsparse.sparse_mapping import build_kernel_map, downsample_coords
+    one = torch.tensor([[0, 5, 5, 5]], dtype=torch.int32, device="cuda")
+    km = build_kernel_map(one, 3, 1)
+    assert km.knnz.cpu().tolist() == [0] * 13 + [1] + [0] * 13 and km.in_map.cpu().tolist() == [0]
+    neg = torch.tensor([[0, -3, 0, 7], [0, -4, 1, 6], [1, -3, 0, 7]], dtype=torch.int32, device="cuda")
+    assert downsample_coords(neg, 2).cpu().tolist() == [[0, -2, 0, 3], [1, -2, 0, 3]]     # floor division, batch kept apart
+    with pytest.raises(TypeError):
+        build_kernel_map(one.long(), 3, 1)
+    with pytest.raises(RuntimeError):
+        build_kernel_map(one.cpu(), 3, 1)
+
+
+def test_maps_drive_spconv_like_a_dense_convolution():
+    """kernel map -> spconv == dense conv3d evaluated at the occupied voxels (submanifold and stride-2 layers)."""
+    import torch.nn.functional as F
+    from dgsparse.sparse_mapping import build_kernel_map
+    rng = np.random.default_rng(7)
+    E, c_in, c_out = 12, 8, 16
+    in_c = random_coords(rng, 500, 1, E)
+    n = in_c.shape[0]
+    feats = torch.tensor(rng.uniform(-1, 1, (n, c_in)), dtype=torch.float32, device="cuda")
+    dense = torch.zeros(1, c_in, E, E, E, device="cuda")
+    ic = torch.from_numpy(in_c).cuda().long()
+    dense[0, :, ic[:, 1], ic[:, 2], ic[:, 3]] = feats.T
+    for ks, st in ((3, 1), (2, 2)):
+        W = torch.tensor(rng.uniform(-1, 1, (ks ** 3, c_in, c_out)), dtype=torch.float32, device="cuda")
+        km = build_kernel_map(torch.from_numpy(in_c).cuda(), ks, st)
+        out = torch.ops.dgsparse_spconv.spconv(feats, W, km.kpos, km.qkpos, km.in_map, km.out_map, km.out_nnz, km.sum_nnz,
+                                               False, False)                       # exact fp32 path
+        w5 = W.reshape(ks, ks, ks, c_in, c_out).permute(4, 3, 0, 1, 2).contiguous()   # [c_out, c_in, kx, ky, kz]
+        ref = F.conv3d(dense.double(), w5.double(), stride=st, padding=(ks - 1) // 2 if st == 1 else 0)
+        oc = km.out_coords.long()
+        want = ref[0][:, oc[:, 1], oc[:, 2], oc[:, 3]].T
+        assert torch.allclose(out.double(), want, rtol=1e-5, atol=1e-5), (ks, st)

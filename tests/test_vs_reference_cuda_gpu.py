@@ -100,3 +100,55 @@ def test_sddmm_cuda_same_as_reference(R, L, graphs, K):
     torch.cuda.synchronize()
     assert_close_f32(ours2.cpu().numpy(), ref2.cpu().numpy(), what=f"sddmm coo K={K} vs reference CUDA",
                      scale=float(K) ** 0.5)
+
+
+@pytest.mark.parametrize("nv", [1, 2, 8, 32])
+@pytest.mark.parametrize("alg", [0, 1, 2, 3])   # ALG_CSR_SCALAR, ALG_CSR_VECTOR, ALG_COO_SCALAR, ALG_COO_VECTOR
+def test_older_api_cuda_csr_coo_spmm(R, L, oracle, graphs, alg, nv):
+    """cuda_csr_coo_spmm (src/ge-spmm/gespmm_v2.h:19-23), row-major: ours vs the reference's, and vs the oracle."""
+    M, Kc = 3000, 2500
+    rowptr, col = graphs.random_csr(M, Kc, 60000, 31 + nv, empty_frac=0.2, hub=1)
+    val = graphs.uniform(col.size, 1, 0.5, 1.5)
+    B = graphs.uniform(Kc * nv, 2, -1.0, 1.0).reshape(Kc, nv)
+    row = np.repeat(np.arange(M, dtype=np.int32), np.diff(rowptr))
+    d_rp, d_row, d_col, d_val, d_B = dev(rowptr), dev(row), dev(col), dev(val), dev(B)
+    ours = torch.full((M, nv), float("nan"), device="cuda")
+    ref = torch.zeros(M, nv, device="cuda")      # the reference's COO algorithms accumulate with atomics
+    torch.cuda.synchronize()
+    args = (alg, 0, M, Kc, int(col.size), nv, d_rp.data_ptr(), d_row.data_ptr(), d_col.data_ptr(), d_val.data_ptr(),
+            d_B.data_ptr())
+    L.lib.cuda_csr_coo_spmm(*args, ours.data_ptr())
+    R.cuda_csr_coo_spmm(*args, ref.data_ptr())
+    torch.cuda.synchronize()
+    want = oracle.spmm(rowptr, col, val, B)
+    assert_close_f32(ours.cpu().numpy(), want, oracle.spmm_f64(rowptr, col, val, B), what=f"older api alg={alg} nv={nv}")
+    assert_close_f32(ref.cpu().numpy(), want, oracle.spmm_f64(rowptr, col, val, B), what=f"reference alg={alg} nv={nv}")
+    if alg >= 2:   # COO entry without a row pointer: rebuilt from rowIdx
+        ours2 = torch.full((M, nv), float("nan"), device="cuda")
+        L.lib.cuda_csr_coo_spmm(alg, 0, M, Kc, int(col.size), nv, None, d_row.data_ptr(), d_col.data_ptr(), d_val.data_ptr(),
+                                d_B.data_ptr(), ours2.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(ours2.cpu().numpy(), ours.cpu().numpy())
+
+
+@pytest.mark.parametrize("layout", [0, 1])      # 0 = column-major, 1 = row-major (gespmm_v2.h:31-33)
+def test_older_api_cuda_csr_spmm(R, L, oracle, graphs, layout):
+    M, Kc, nv = 2000, 1800, 16
+    rowptr, col = graphs.random_csr(M, Kc, 40000, 5, empty_frac=0.1, hub=1)
+    val = graphs.uniform(col.size, 1, 0.5, 1.5)
+    B = graphs.uniform(Kc * nv, 2, -1.0, 1.0).reshape(Kc, nv)
+    Bd = dev(B if layout == 1 else np.ascontiguousarray(B.T))
+    d_rp, d_col, d_val = dev(rowptr), dev(col), dev(val)
+    ours = torch.full((M * nv,), float("nan"), device="cuda")
+    ref = torch.zeros(M * nv, device="cuda")
+    args = (0, layout, M, Kc, nv, int(col.size), d_rp.data_ptr(), d_col.data_ptr(), d_val.data_ptr(), Bd.data_ptr())
+    L.lib.cuda_csr_spmm(*args, ours.data_ptr())
+    R.cuda_csr_spmm(*args, ref.data_ptr())
+    torch.cuda.synchronize()
+    shape = (M, nv) if layout == 1 else (nv, M)
+    o, r = ours.cpu().numpy().reshape(shape), ref.cpu().numpy().reshape(shape)
+    if layout == 0:
+        o, r = o.T, r.T
+    want = oracle.spmm(rowptr, col, val, B)
+    assert_close_f32(o, want, oracle.spmm_f64(rowptr, col, val, B), what=f"cuda_csr_spmm layout={layout}")
+    assert_close_f32(r, want, oracle.spmm_f64(rowptr, col, val, B), what=f"reference cuda_csr_spmm layout={layout}")
