@@ -353,10 +353,27 @@ def main():
         h_C = torch.empty(M, N, dtype=torch.float32).pin_memory()
         red = L.MAX if "max" in wl["op"] else L.SUM
 
-        def e2e_step():
-            L.check(L.lib.dgs_spmm_csr_host(M, M, N, nnz, h_rp.data_ptr(), h_cc.data_ptr(),
-                                            h_val.data_ptr() if h_val is not None else None, h_B.data_ptr(),
-                                            h_C.data_ptr(), None, red, L.MUL), "dgs_spmm_csr_host")
+        if world == 1:
+            def e2e_step():
+                L.check(L.lib.dgs_spmm_csr_host(M, M, N, nnz, h_rp.data_ptr(), h_cc.data_ptr(),
+                                                h_val.data_ptr() if h_val is not None else None, h_B.data_ptr(),
+                                                h_C.data_ptr(), None, red, L.MUL), "dgs_spmm_csr_host")
+            h2d = 4 * (M + 1) + 4 * nnz + (4 * nnz if val is not None else 0) + 4 * M * N
+            d2h = 4 * M * N
+            api = "dgs_spmm_csr_host (include/dgsparse_b200.h): pinned host CSR + B in, C out, every step"
+        else:
+            # host operands on every rank; the CSR crosses PCIe once per box (1/world per rank) and is replicated by an
+            # NCCL all-gather over NVLink; every rank gets its own C panel back on the host
+            from dgsparse.distributed import HostColumnShardedSpMM
+            hop = HostColumnShardedSpMM(M, nnz, N, val is not None, dev, reduce=red, compute=L.MUL, mode=args.mode)
+
+            def e2e_step():
+                hop(h_rp, h_cc, h_val, h_B, h_C)
+            tot = torch.tensor([hop.h2d_bytes + 4 * M * N, hop.d2h_bytes], device=dev, dtype=torch.float64)
+            dist.all_reduce(tot)
+            h2d, d2h = int(tot[0].item()), int(tot[1].item())
+            api = ("dgsparse.distributed.HostColumnShardedSpMM: pinned host CSR slice (1/world per rank) + B panel in, "
+                   "NCCL all-gather of col/val over NVLink, fused peer-store SpMM, own C panel out; bytes are whole-job totals")
         for _ in range(2):
             e2e_step()
         barrier()
@@ -368,10 +385,8 @@ def main():
         te = torch.tensor([(time.perf_counter() - t0) / ksteps], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        h2d = 4 * (M + 1) + 4 * nnz + (4 * nnz if val is not None else 0) + 4 * M * N
         e2e = {"value": flop / float(te.item()) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 4 * M * N, "ms_per_step": float(te.item()) * 1e3, "steps": ksteps,
-               "api": "dgs_spmm_csr_host (include/dgsparse_b200.h): pinned host CSR + B in, C out, every step"}
+               "d2h_bytes_per_step": d2h, "ms_per_step": float(te.item()) * 1e3, "steps": ksteps, "api": api}
 
     # --- the reference's own CUDA kernels (oracle/_ref/libref_cuda.so, built unmodified for sm_100a) on the
     #     same device buffers, same timing loop: the "vs reference CUDA" comparison of SURVEY.md §8d.

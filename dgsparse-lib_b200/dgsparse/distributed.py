@@ -123,3 +123,66 @@ class ColumnShardedSpMM:
         for p in self._opened:
             self._lib.lib.dgs_ipc_close(p)
         self._opened = []
+
+
+def nnz_chunks(nnz: int, world: int):
+    """Equal, padded slices of the nonzero stream: (chunk, [(lo, hi)] per rank with hi clipped to nnz)."""
+    chunk = (nnz + world - 1) // world
+    return chunk, [(min(nnz, r * chunk), min(nnz, (r + 1) * chunk)) for r in range(world)]
+
+
+class HostColumnShardedSpMM:
+    """The column-sharded SpMM for HOST-resident operands (the multi-GPU counterpart of dgs_spmm_csr_host).
+
+    Every rank needs the whole CSR, but the CSR needs to cross PCIe only once per BOX: rank r uploads the r-th
+    1/world slice of col / val (plus rowptr and its own B panel), one NCCL all-gather per array replicates the slices
+    over NVLink (~15x the bandwidth of one PCIe link), then the fused peer-store SpMM runs and the rank's own C panel
+    returns to the host.  Per rank and step at world = 8 on the reddit-like config: 182 MB over PCIe instead of 977 MB.
+    """
+
+    def __init__(self, M: int, nnz: int, n_local: int, has_value: bool, device, reduce: int = 0, compute: int = 2,
+                 group=None, mode: Optional[str] = None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.M, self.nnz, self.n_local = M, nnz, n_local
+        self.chunk, spans = nnz_chunks(nnz, self.world)
+        self.lo_nnz, self.hi_nnz = spans[self.rank]
+        padded = self.chunk * self.world
+        self.d_rowptr = torch.empty(M + 1, dtype=torch.int32, device=device)
+        self.d_col = torch.zeros(padded, dtype=torch.int32, device=device)
+        self.d_val = torch.zeros(padded, dtype=torch.float32, device=device) if has_value else None
+        self.d_B = None
+        self.op = ColumnShardedSpMM(self.d_rowptr, self.d_col[:nnz], self.d_val[:nnz] if has_value else None, n_local,
+                                    reduce=reduce, compute=compute, group=group, mode=mode)
+        self.h2d_bytes = 4 * (M + 1) + (self.hi_nnz - self.lo_nnz) * (8 if has_value else 4)
+        self.d2h_bytes = 4 * M * n_local
+
+    def __call__(self, h_rowptr, h_col, h_val, h_B_local, h_C_local):
+        """All arguments are host tensors (pinned for asynchronous copies); h_C_local [M, n_local] receives this
+        rank's panel.  Synchronises before returning."""
+        lo, hi, r = self.lo_nnz, self.hi_nnz, self.rank
+        self.d_rowptr.copy_(h_rowptr, non_blocking=True)
+        mine_c = self.d_col[r * self.chunk:(r + 1) * self.chunk]
+        mine_c[:hi - lo].copy_(h_col[lo:hi], non_blocking=True)
+        if self.d_val is not None:
+            mine_v = self.d_val[r * self.chunk:(r + 1) * self.chunk]
+            mine_v[:hi - lo].copy_(h_val[lo:hi], non_blocking=True)
+        if self.d_B is None:
+            self.d_B = torch.empty(h_B_local.shape, dtype=torch.float32, device=self.d_col.device)
+        self.d_B.copy_(h_B_local, non_blocking=True)
+        if self.world > 1:   # in-place all-gather: every rank's slice already sits at its final offset
+            dist.all_gather_into_tensor(self.d_col, mine_c, group=self.group)
+            if self.d_val is not None:
+                dist.all_gather_into_tensor(self.d_val, mine_v, group=self.group)
+        out = self.op(self.d_B)
+        if self.op.mode == "nccl":
+            panel = out[self.rank]
+        else:
+            panel = out[:, self.op.lo:self.op.hi]
+        h_C_local.copy_(panel, non_blocking=True)
+        torch.cuda.current_stream(self.d_col.device).synchronize()
+        return h_C_local
+
+    def close(self):
+        self.op.close()

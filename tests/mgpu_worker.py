@@ -46,6 +46,23 @@ def main():
                 print("PEER MAPPING UNAVAILABLE:", getattr(op, "_peer_error", "?"), flush=True)
             dist.barrier()
             op.close()
+    # host-resident operands: sliced upload + NVLink all-gather of the CSR, own panel back to the host
+    from dgsparse.distributed import HostColumnShardedSpMM
+    hp = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_rp, h_cc, h_vv = hp(rowptr), hp(col), hp(val)
+    h_B = hp(Bfull[:, rank * n_local:(rank + 1) * n_local])
+    h_C = torch.empty(M, n_local, dtype=torch.float32).pin_memory()
+    hop = HostColumnShardedSpMM(M, int(col.size), n_local, True, dev)
+    for it in range(2):
+        h_C.fill_(float("nan"))
+        hop(h_rp, h_cc, h_vv, h_B, h_C)
+    ok = torch.equal(h_C, ref[:, rank * n_local:(rank + 1) * n_local].cpu())
+    flag = torch.tensor([int(ok)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"host-sharded path identical={bool(flag.item())} mode={hop.op.mode}", flush=True)
+    assert flag.item() == 1
+    hop.close()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

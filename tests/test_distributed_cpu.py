@@ -40,6 +40,16 @@ def test_column_shard_host_logic_world2():
     assert all(ret[r] for r in range(world))
 
 
+def test_nnz_chunks_cover_the_stream():
+    sys.path.insert(0, os.path.join(ROOT, "dgsparse-lib_b200"))
+    from dgsparse.distributed import nnz_chunks
+    for nnz, world in ((114615892, 8), (10, 4), (3, 8), (0, 2), (16, 4)):
+        chunk, spans = nnz_chunks(nnz, world)
+        assert chunk * world >= nnz and len(spans) == world
+        assert spans[0][0] == 0 and spans[-1][1] == nnz
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and all(hi - lo <= chunk for lo, hi in spans)
+
+
 def test_shard_columns_rejects_ragged_split():
     sys.path.insert(0, os.path.join(ROOT, "dgsparse-lib_b200"))
     from dgsparse.distributed import shard_columns
