@@ -213,7 +213,21 @@ def reference_cuda_run(wl, M, N, nnz, rp, cc, vv, B, D1, D2, our_step, steps, wa
             R.spmm_cuda(M, N, rp.data_ptr(), cc.data_ptr(), vv.data_ptr(), B.data_ptr(), ref_out.data_ptr())
         what = "spmm_cuda -> gespmmCsrSpMM (src/ge-spmm/gespmm.cc:29-123)"
     else:
-        return {"unavailable": f"the reference's C ABI has no {wl['op']} (gspmm-fp is a torch pybind module)"}
+        # gspmm-fp: the reference's own pybind module, built unmodified by oracle/build_ref_gspmm.sh
+        G = oracle.ref_gspmm_module()
+        if G is None:
+            return {"unavailable": "oracle/_ref/spmm.so (reference gspmm-fp module) was not built"}
+        import dgsparse._lib as L
+        import dgsparse._kernels as K
+        red = "MAX" if "max" in wl["op"] else "MEAN" if "mean" in wl["op"] else "SUM"
+        our_out = K.spmm(rp, cc, vv, B, getattr(L, red), L.MUL)
+        holder = {}
+
+        def ref_step():
+            holder["out"] = G.GSpMM_u_e(rp, cc, vv, B, getattr(G.REDUCEOP, red), G.COMPUTEOP.MUL)
+        ref_step()
+        ref_out = holder["out"]
+        what = f"GSpMM_u_e(..., {red}, MUL) (src/gspmm-fp/gspmm.cu:406-473; allocates its output every call)"
     for _ in range(warmup):
         ref_step()
     torch.cuda.synchronize()
@@ -224,6 +238,7 @@ def reference_cuda_run(wl, M, N, nnz, rp, cc, vv, B, D1, D2, our_step, steps, wa
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    ref_out = locals().get("holder", {}).get("out", ref_out)
     a, b = our_out.reshape(-1), ref_out.reshape(-1)
     err = float(((a - b).abs() / b.abs().clamp_min(1e-6)).max().item())
     return {"kernel": what, "ms_per_step": ms, "value": flop / (ms * 1e-3) / 1e9, "unit": "GFLOP/s",

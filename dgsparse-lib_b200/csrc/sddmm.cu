@@ -198,7 +198,10 @@ __global__ void __launch_bounds__(kSdThreads) sddmm_kernel(const SddmmArgs a) {
 // TMA unit serialises small random copies; the first cp.async ring did its index math serially per edge and was
 // instruction-latency bound, time inversely proportional to the warp count.)
 // D1 rows are streamed once -> L2 evict_first policy; D2 rows are the reused operand and keep the default policy
-// (a fractional evict_last policy on D2, 0.3 .. 0.9 of L2, was measured and changed nothing: 0.198 - 0.205 ms).
+// (a fractional evict_last policy on D2, 0.3 .. 0.9 of L2, was measured and changed nothing: 0.198 - 0.205 ms;
+// column-range passes that keep one slice of D2 L2-resident per pass, with the pass's edges compacted by shuffles,
+// were measured too: 0.208 ms for 1 pass, 0.277 / 0.348 / 0.413 ms for 2 / 3 / 4 — the kernel is bound by per-warp
+// issue latency, not by the 909 MB of DRAM traffic, so re-walking the edge list costs more than the misses it saves).
 constexpr int kRgNB = 4;          // edges per batch: one per 8-lane group of the copying warp
 constexpr int kRgBPS = 32 / kRgNB; // batches per 32-edge superbatch
 constexpr int kRgMetaBytes = 2 * kRgBPS * 4 + 2 * 32 * 4;   // two superbatches of packed slots + degrees

@@ -124,6 +124,26 @@ def ref_cuda_lib():
         return _ref_cuda
 
 
+_ref_gspmm = None
+
+
+def ref_gspmm_module():
+    """The reference's own gspmm-fp pybind module `spmm` (oracle/_ref/spmm.so, built by oracle/build_ref_gspmm.sh from
+    src/gspmm-fp/gspmm.{cu,cc} unmodified) or None.  GSpMM_u_e(rowptr, colind, edge_val, feat, REDUCEOP, COMPUTEOP) and
+    GSpMM_u(rowptr, colind, feat, REDUCEOP) on CUDA tensors (src/gspmm-fp/gspmm.cc:27-44)."""
+    global _ref_gspmm
+    with _lock:
+        path = os.path.join(_HERE, "_ref", "spmm.so")
+        if _ref_gspmm is None and os.path.exists(path):
+            import importlib.util
+            import torch  # noqa: F401  (libtorch must be loaded before the extension)
+            spec = importlib.util.spec_from_file_location("spmm", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _ref_gspmm = mod
+        return _ref_gspmm
+
+
 def num_threads():
     return int(lib().oracle_num_threads())
 
