@@ -712,6 +712,197 @@ __global__ void __launch_bounds__(256) spconv_wgrad_kernel(const SpconvArgs a, c
   if (cur_k >= 0) flush(cur_k);
 }
 
+// ---- kernel gradient on the tensor cores (tf32) ----------------------------------------------------------------------
+// dW[k] = X_k^T . G_k where X_k / G_k are the gathered input / output-gradient rows of the pairs of offset k: a GEMM whose
+// contraction axis is the PAIR axis.  The gathered 128-pair tiles are written to shared memory exactly as in the forward
+// ([32-channel block][128 pairs][128 B], but with the SWIZZLE_128B_BASE32B pattern) and handed to tcgen05.mma as MN-major
+// operands: the 128 B row of a pair is 32 consecutive M (or N) elements, eight pair rows are one K = 8 instruction, LBO =
+// the 16 KB between channel blocks, SBO = 512 B between 4-row groups.  16 MMAs consume a tile; the fp32 accumulator (c_in block x c_out block)
+// stays in TMEM across ALL tiles of an offset and is flushed with red.global.add.v4 only when the offset changes or the
+// CTA's run ends.  Warps 0-3 gather (cp.async, zero-fill for padding pairs), warp 4 issues the MMAs; the gather warps also
+// do the rare flush.  M is always 128 (c_in blocks narrower than 128 are zero-filled by the gather), so accumulator row r
+// lives in TMEM lane r.
+constexpr int kWgtMaxStages = 3;
+
+// MN-major descriptor for 32-bit operands: SWIZZLE_128B_BASE32B (layout type 1) is the only MN-major layout tcgen05 accepts
+// for tf32 (cute: Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> over [4 K rows][128 B]): the 32-byte chunk index of a row is
+// XORed with (K row & 3); LBO = bytes between 32-element MN blocks, SBO = 512 B between 4-row K groups.
+__device__ __forceinline__ uint64_t umma_desc_mn128_b32(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(512 >> 4) << 32) |
+         (1ull << 46) | (1ull << 61);
+}
+
+struct WgradTcArgs {
+  SpconvArgs a;
+  const float *dout;
+  int64_t ld_dout;
+  float *dW;
+  int MB, NBk;        // rows (c_in) and columns (c_out) of dW handled by this CTA's blockIdx.y / .z: 128, <= 128
+  int n_stages;
+  int m64_mode;       // experiment: TMEM row mapping hypothesis for M = 64 (1: lane = row, 2: 16 rows per quadrant)
+};
+
+__global__ void __launch_bounds__(160, 1) spconv_wgrad_tc_kernel(const WgradTcArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t s_full[kWgtMaxStages], s_empty[kWgtMaxStages], s_accfull, s_accempty;
+  __shared__ uint32_t s_tmem;
+  const SpconvArgs &a = g.a;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = g.n_stages;
+  const int mblk = g.MB / 32, nblk = (g.NBk + 31) / 32;          // 32-channel blocks of the two operands
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t blk_bytes = kTileM * kAtomBytes;                 // 16 KB: [128 pairs][128 B]
+  const uint32_t stage_bytes = (uint32_t)(mblk + nblk) * blk_bytes;
+  const int ci0 = blockIdx.y * g.MB, co0 = blockIdx.z * g.NBk;
+  const int tmem_cols = g.NBk <= 32 ? 32 : g.NBk <= 64 ? 64 : 128;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) { mbar_init(&s_full[s], 128); mbar_init(&s_empty[s], 1); }
+    mbar_init(&s_accfull, 1); mbar_init(&s_accempty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(&s_tmem, (uint32_t)tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  const int n_tiles = a.n_map_tiles + a.n_id_tiles;
+  const int t_begin = blockIdx.x * a.tiles_per_cta;
+  const int n_my = max(0, min(n_tiles, t_begin + a.tiles_per_cta) - t_begin);
+
+  if (warp < 4) {
+    // ================= gather (+ the rare flush) =================
+    const int cpr = (mblk + nblk) * 8;   // 16-byte chunks per pair: X block chunks first, then G block chunks
+    TileCursor cur;
+    int next_in = -1, next_out = -1;
+    if (n_my > 0) {
+      cur.init(a, t_begin);
+      cur.seek(a, t_begin);
+      const int p = cur.pbase + warp * 32 + lane;
+      if (p < cur.pend) { next_in = cur.identity ? p : __ldg(a.imap + p); next_out = cur.identity ? p : __ldg(a.omap + p); }
+    }
+    int na = 0, cur_k = -1, n_flush = 0;
+
+    auto flush = [&](int k, int upto) {
+      // hand over every gathered tile, wait for the MMA warp's commit of the accumulator, add it into dW[k]
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fence_proxy_async_smem();
+      for (; na < upto; na++) mbar_arrive(&s_full[na % S]);
+      mbar_wait(&s_accfull, (uint32_t)n_flush & 1u);
+      tc_fence_after();
+      int row = warp * 32 + lane;                // accumulator row (c_in index within the block) = TMEM lane
+      bool has_row = true;
+      if (g.MB == 64) {
+        if (g.m64_mode == 2) { row = warp * 16 + lane; has_row = lane < 16; }
+        else { has_row = warp < 2; }
+      }
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+      float *wrow = g.dW + ((int64_t)k * a.c_in + ci0 + row) * a.c_out + co0;
+      for (int c0 = 0; c0 < g.NBk; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        if (has_row && ci0 + row < a.c_in) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            if (co0 + c0 + j + 3 < a.c_out) red_add_v4(wrow + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            else {
+#pragma unroll
+              for (int e = 0; e < 4; e++)
+                if (co0 + c0 + j + e < a.c_out) atomicAdd(wrow + c0 + j + e, v[j + e]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_accempty);
+      n_flush++;
+    };
+
+    for (int i = 0; i < n_my; i++) {
+      const int s = i % S;
+      const int my_in = next_in, my_out = next_out;
+      const int tile_k = cur.offset(a);
+      if (i + 1 < n_my) {
+        cur.seek(a, t_begin + i + 1);
+        const int p = cur.pbase + warp * 32 + lane;
+        next_in = next_out = -1;
+        if (p < cur.pend) { next_in = cur.identity ? p : __ldg(a.imap + p); next_out = cur.identity ? p : __ldg(a.omap + p); }
+      }
+      if (tile_k != cur_k) {
+        if (cur_k >= 0) flush(cur_k, i);
+        cur_k = tile_k;
+      }
+      if (i >= S) mbar_wait(&s_empty[s], (uint32_t)(i / S - 1) & 1u);
+      const uint32_t sX = base + (uint32_t)s * stage_bytes;
+      int rl = lane / cpr, cc = lane % cpr;
+      const int drl = 32 / cpr, dcc = 32 % cpr;
+      for (int it = 0; it < cpr; it++) {
+        const int r = warp * 32 + rl;
+        const bool is_x = cc < mblk * 8;
+        const int blk = is_x ? (cc >> 3) : ((cc - mblk * 8) >> 3), c = cc & 7;
+        const int in_r = __shfl_sync(0xffffffffu, my_in, rl), out_r = __shfl_sync(0xffffffffu, my_out, rl);
+        const int src_row = is_x ? in_r : out_r;   // (the select must happen in the READING lane)
+        const int ch = (is_x ? ci0 : co0) + blk * 32 + c * 4;
+        const bool ok = src_row >= 0 && ch < (is_x ? a.c_in : a.c_out);
+        const float *src = is_x ? a.in + (int64_t)src_row * a.ld_in + ch : g.dout + (int64_t)src_row * g.ld_dout + ch;
+        const uint32_t dst = sX + (uint32_t)((is_x ? 0 : mblk) + blk) * blk_bytes + (uint32_t)r * kAtomBytes +
+                             (uint32_t)((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));   // BASE32B swizzle
+        cp_async16_zfill(dst, ok ? (const void *)src : (const void *)a.in, ok ? 16u : 0u);
+        rl += drl; cc += dcc;
+        if (cc >= cpr) { cc -= cpr; rl += 1; }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (i - na >= 1) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        fence_proxy_async_smem();
+        mbar_arrive(&s_full[na % S]);
+        na++;
+      }
+    }
+    if (cur_k >= 0) flush(cur_k, n_my);
+  } else {
+    // ================= MMA issue =================
+    if (lane == 0) {
+      // D fp32, A/B tf32, both MN-major (bits 15, 16), N >> 3, M >> 4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(g.NBk >> 3) << 17) |
+                             ((uint32_t)(g.MB >> 4) << 24);
+      TileCursor cur;
+      if (n_my > 0) cur.init(a, t_begin);
+      int cur_k = -1, n_flush = 0;
+      bool first = true;
+      for (int i = 0; i < n_my; i++) {
+        const int s = i % S;
+        cur.seek(a, t_begin + i);
+        const int tile_k = cur.offset(a);
+        if (tile_k != cur_k) {
+          if (cur_k >= 0) {
+            umma_commit(&s_accfull);                                   // accumulator of the previous offset complete
+            mbar_wait(&s_accempty, (uint32_t)n_flush & 1u);            // ... and drained by the flush
+            n_flush++;
+          }
+          cur_k = tile_k;
+          first = true;
+        }
+        mbar_wait(&s_full[s], (uint32_t)(i / S) & 1u);
+        tc_fence_after();
+        const uint32_t sX = base + (uint32_t)s * stage_bytes, sG = sX + (uint32_t)mblk * blk_bytes;
+        for (int ks = 0; ks < kTileM / 8; ks++) {
+          const uint64_t ad = umma_desc_mn128_b32(sX + (uint32_t)ks * 1024u, blk_bytes);
+          const uint64_t bd = umma_desc_mn128_b32(sG + (uint32_t)ks * 1024u, blk_bytes);
+          umma<0>(tmem, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+        }
+        first = false;
+        umma_commit(&s_empty[s]);
+      }
+      if (cur_k >= 0) umma_commit(&s_accfull);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+}
+
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 struct TcGeometry {
@@ -861,7 +1052,6 @@ cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspac
 cudaError_t spconv_wgrad(int k_vol, int c_in, int c_out, const int *kpos, const int *qkpos, const int *imap, const int *omap,
                          int64_t sum_nnz, const float *in, int64_t ld_in, int in_rows, const float *dout, int64_t ld_dout,
                          float *dW, int precision, int separate_mid, cudaStream_t stream) {
-  (void)precision;   // fp32 FMA for every precision: the gradient of the weights is the small, accuracy-critical output
   if (k_vol <= 0 || c_in <= 0 || c_out <= 0 || sum_nnz % kTileM != 0) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)k_vol * c_in * c_out, stream);
   if (e != cudaSuccess) return e;
@@ -875,6 +1065,34 @@ cudaError_t spconv_wgrad(int k_vol, int c_in, int c_out, const int *kpos, const 
   const int n_tiles = a.n_map_tiles + a.n_id_tiles;
   if (n_tiles == 0) return cudaSuccess;
   ProfileScope prof(6, stream);
+  // tensor path (tf32 operands, fp32 accumulation in TMEM) for the tf32 / bf16 precisions when rows are 16-byte aligned
+  const bool tc_ok = precision != SPCONV_FP32 && c_in % 4 == 0 && c_out % 4 == 0 && ld_in % 4 == 0 && ld_dout % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(dW) & 15) == 0 && !getenv("DGS_SPCONV_WGRAD_SIMT");
+  if (tc_ok) {
+    WgradTcArgs g;
+    g.a = a; g.dout = dout; g.ld_dout = ld_dout; g.dW = dW;
+    g.MB = 128;   // always M = 128 (rows beyond c_in are zero-filled): one accumulator row per TMEM lane
+    g.m64_mode = 0;
+    if (const char *e = getenv("DGS_WGRAD_M64")) { g.m64_mode = atoi(e); if (g.m64_mode && c_in <= 64) g.MB = 64; }
+    const int n16 = round_up(c_out, 16);
+    g.NBk = n16 <= 128 ? n16 : 128;
+    const int by = (c_in + g.MB - 1) / g.MB, bz = (c_out + g.NBk - 1) / g.NBk;
+    const size_t stage_bytes = (size_t)(g.MB / 32 + (g.NBk + 31) / 32) * kTileM * kAtomBytes;
+    int S = (int)((220u * 1024u) / stage_bytes);
+    if (S > kWgtMaxStages) S = kWgtMaxStages;
+    if (S >= 2) {
+      g.n_stages = S;
+      int ctas = device_sm_count() / (by * bz);
+      if (ctas < 1) ctas = 1;
+      g.a.tiles_per_cta = (n_tiles + ctas - 1) / ctas;
+      const size_t smem = 1024 + (size_t)S * stage_bytes;
+      if ((e = cudaFuncSetAttribute(spconv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      dim3 grid((n_tiles + g.a.tiles_per_cta - 1) / g.a.tiles_per_cta, by, bz);
+      spconv_wgrad_tc_kernel<<<grid, 160, smem, stream>>>(g);
+      return cudaGetLastError();
+    }
+  }
   const int by = (c_in + kWgBlk - 1) / kWgBlk, bz = (c_out + kWgBlk - 1) / kWgBlk;
   int tpc = n_tiles * by * bz / (device_sm_count() * 6);
   if (tpc < 1) tpc = 1;

@@ -164,7 +164,33 @@ def test_torch_op_autograd(arch80):
     scale_o = float(o64.abs().max()); scale_x = float(x64.grad.abs().max()); scale_w = float(w64.grad.abs().max())
     assert (out.double() - o64).abs().max().item() <= tol * scale_o * 4
     assert (x.grad.double() - x64.grad).abs().max().item() <= tol * scale_x * 4
-    assert (w.grad.double() - w64.grad).abs().max().item() <= 1e-5 * scale_w * 4     # kernel gradient is fp32 FMA
+    assert (w.grad.double() - w64.grad).abs().max().item() <= tol * scale_w * 4     # tf32 tensor path / fp32 FMA
+
+
+@pytest.mark.parametrize("c_in,c_out", [(64, 64), (32, 96), (128, 128), (4, 64), (200, 72), (64, 256)])
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_kernel_gradient(precision, c_in, c_out):
+    """dW[k] = sum_p in[imap[p]]^T (x) gout[omap[p]]: tensor-core (tf32, MN-major operands) and fp32 FMA kernels vs fp64."""
+    import dgsparse.spconv as S
+    rng = np.random.default_rng(c_in * 7 + c_out)
+    in_nnz, out_nnz, k_vol = 2000, 1800, 27
+    imap, omap, knnz = make_maps(rng, in_nnz, out_nnz, k_vol, 0.3)
+    kpos, qkpos, sum_nnz = S.quantize_kpos(torch.from_numpy(knnz).cuda())
+    x = rng.uniform(-1, 1, (in_nnz, c_in)).astype(np.float32)
+    g = rng.uniform(-1, 1, (out_nnz, c_out)).astype(np.float32)
+    w = np.zeros((k_vol, c_in, c_out), np.float32)
+    _, gk = S.spconv_bwd_fused(dev(g), dev(x), dev(w), kpos, qkpos, dev(imap), dev(omap), sum_nnz, False, True,
+                               need_in=False, precision=precision)
+    torch.cuda.synchronize()
+    kp = kpos.cpu().numpy()
+    want = np.zeros((k_vol, c_in, c_out))
+    bound = np.zeros_like(want)
+    for k in range(k_vol):
+        s, e = int(kp[k]), int(kp[k + 1])
+        if e > s:
+            want[k] = x[imap[s:e]].astype(np.float64).T @ g[omap[s:e]].astype(np.float64)
+            bound[k] = np.abs(x[imap[s:e]]).astype(np.float64).T @ np.abs(g[omap[s:e]]).astype(np.float64)
+    check(gk.cpu().numpy(), want, bound, precision, f"dW {c_in}x{c_out}")
 
 
 def test_errors():
