@@ -246,6 +246,24 @@ int dgs_kmap_build(int in_nnz, const int *in_coords, int out_nnz, const int *out
                                knnz, kpos, qkpos, workspace, workspace_bytes, (cudaStream_t)stream), "dgs_kmap_build");
 }
 
+size_t dgs_kmap_expand_workspace_bytes(int in_nnz, int k_vol) { return dgs::kmap_expand_workspace_bytes(in_nnz, k_vol); }
+
+int dgs_kmap_downsample_expand(int in_nnz, const int *in_coords, int ksx, int ksy, int ksz, int sx, int sy, int sz, int px,
+                               int py, int pz, const int *lo, const int *hi, int *out_coords, int *out_nnz_dev,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+  return ok_or(dgs::kmap_downsample_expand(in_nnz, in_coords, ksx, ksy, ksz, sx, sy, sz, px, py, pz, lo, hi, out_coords,
+                                           out_nnz_dev, workspace, workspace_bytes, (cudaStream_t)stream),
+               "dgs_kmap_downsample_expand");
+}
+
+int dgs_kmap_build_ex(int in_nnz, const int *in_coords, int out_nnz, const int *out_coords, int ksx, int ksy, int ksz,
+                      int sx, int sy, int sz, int px, int py, int pz, int subm, int q, int skip_mid, int *imap, int *omap,
+                      int *knnz, int *kpos, int *qkpos, void *workspace, size_t workspace_bytes, void *stream) {
+  return ok_or(dgs::kmap_build_ex(in_nnz, in_coords, out_nnz, out_coords, ksx, ksy, ksz, sx, sy, sz, px, py, pz, subm, q,
+                                  skip_mid, imap, omap, knnz, kpos, qkpos, workspace, workspace_bytes, (cudaStream_t)stream),
+               "dgs_kmap_build_ex");
+}
+
 // ---- host-buffer entry points --------------------------------------------------------------------
 namespace {
 struct HostStage {

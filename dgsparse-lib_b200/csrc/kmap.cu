@@ -8,10 +8,14 @@
 // well-defined product the spconv op consumes (the MinkUNet fixtures' layout): pair lists (imap, omap) grouped by
 // kernel offset, kpos / qkpos, DETERMINISTIC (within an offset the pairs are ordered by output index).
 //
-// Semantics (offset decode order and centring exactly as _queryhash_subm / _queryhash_sp with padding 0):
-//   tap kp = (kx * ksy + ky) * ksz + kz, kx in [0, ksx) ...
-//   stride 1 (submanifold):  out_coords = in_coords;        input = out + (tap - (ks - 1) / 2)
-//   stride s > 1:            out_coords = sorted unique of floor(in / s) (batch kept);   input = out * s + tap
+// Semantics (offset decode order and centring exactly as _queryhash_subm / _queryhash_sp):
+//   tap kp = (kx * ksy + ky) * ksz + kz, kx in [0, ksx) ...;  off(k) = k - (ks-1)/2 (+1 for odd ks > 1)
+//   submanifold:             out_coords = in_coords;        input = out + (tap - (ks - 1) / 2)
+//   plain down-sampling (stride = 1 or ks per axis, padding 0):
+//                            out_coords = sorted unique of floor(in / s) (batch kept);   input = out * s + off(tap)
+//   general layer (coordsDownsampleExpand, any stride / padding / bounds):
+//                            out_coords = sorted unique of (in - off(tap) + pad) / s over exact divisions inside [lo, hi];
+//                            input = out * s - pad + off(tap)
 // Integer, HBM / latency bound: one 64-bit key per coordinate (16 bits per component, biased), an open-addressing
 // hash table of the input keys (2x over-provisioned, linear probing, atomicCAS), one thread per (offset, output) query
 // writing a k-major hit table, an exclusive scan of the hit flags (cub::DeviceScan: position = final pair index, so the
@@ -37,6 +41,45 @@ __device__ __forceinline__ unsigned hash_key(unsigned long long k) {   // 64 -> 
   return (unsigned)k;
 }
 __device__ __forceinline__ int floor_div(int a, int s) { return (a >= 0) ? a / s : -((-a + s - 1) / s); }
+// Offset of tap k along one axis of a strided layer: the decode shared by coordsDownsampleExpand and _queryhash_sp
+// (include/cuda/sparse_mapping.cuh:365-370, :195-200): k - (ks-1)/2, plus 1 for odd ks > 1  ->  k for ks <= 3,
+// k - 1 for ks = 4 and 5, k - 2 for ks = 6 and 7 ...
+__device__ __forceinline__ int tap_offset(int k, int ks) { return k - (ks - 1) / 2 + ((ks % 2 == 0 || ks == 1) ? 0 : 1); }
+
+struct ExpandArgs {
+  int in_nnz, ksx, ksy, ksz, k_vol, sx, sy, sz, px, py, pz;
+  int lo[3], hi[3];
+  const int *in_coords;
+  unsigned long long *keys;   // [in_nnz * k_vol]
+};
+
+// coordsDownsampleExpand (include/cuda/sparse_mapping.cuh:326-401): every (input, tap) proposes the output voxel
+// (in - tap + padding) / stride when that division is exact and the result lies inside [lo, hi]; everything else
+// becomes the empty key (sorts last).  Per-axis padding (the reference reads padding[0] for all three axes).
+__global__ void __launch_bounds__(256) expand_keys_kernel(const ExpandArgs a) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)a.in_nnz * a.k_vol) return;
+  const int i = (int)(t / a.k_vol), k = (int)(t % a.k_vol);
+  const int4 v = __ldg(reinterpret_cast<const int4 *>(a.in_coords) + i);
+  const int cx = v.y - tap_offset(k / (a.ksz * a.ksy), a.ksx) + a.px;
+  const int cy = v.z - tap_offset((k / a.ksz) % a.ksy, a.ksy) + a.py;
+  const int cz = v.w - tap_offset(k % a.ksz, a.ksz) + a.pz;
+  unsigned long long key = kEmptyKey;
+  if (cx % a.sx == 0 && cy % a.sy == 0 && cz % a.sz == 0) {
+    const int ox = cx / a.sx, oy = cy / a.sy, oz = cz / a.sz;
+    if (ox >= a.lo[0] && ox <= a.hi[0] && oy >= a.lo[1] && oy <= a.hi[1] && oz >= a.lo[2] && oz <= a.hi[2])
+      key = pack_key(v.x, ox, oy, oz);
+  }
+  a.keys[t] = key;
+}
+
+// the empty key, if any candidate was rejected, is the last unique key: drop it from the count
+__global__ void drop_empty_key_kernel(int *n_dev, const unsigned long long *keys) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int n = *n_dev;
+    if (n > 0 && keys[n - 1] == kEmptyKey) *n_dev = n - 1;
+  }
+}
 
 __global__ void __launch_bounds__(256) downsample_keys_kernel(int n, const int *__restrict__ c, int sx, int sy, int sz,
                                                               unsigned long long *__restrict__ keys) {
@@ -76,7 +119,7 @@ __global__ void __launch_bounds__(256) hash_insert_kernel(int n, const int *__re
 }
 
 struct QueryArgs {
-  int out_nnz, ksx, ksy, ksz, k_vol, sx, sy, sz, skip_k;
+  int out_nnz, ksx, ksy, ksz, k_vol, sx, sy, sz, skip_k, px, py, pz, subm;
   const int *out_coords;
   unsigned mask;
   const unsigned long long *tkeys;
@@ -93,10 +136,12 @@ __global__ void __launch_bounds__(256) query_kernel(const QueryArgs a) {
   const int4 v = __ldg(reinterpret_cast<const int4 *>(a.out_coords) + o);
   int kx = k / (a.ksz * a.ksy), ky = (k / a.ksz) % a.ksy, kz = k % a.ksz;
   int x, y, z;
-  if (a.sx == 1 && a.sy == 1 && a.sz == 1) {   // _queryhash_subm: centred taps
+  if (a.subm) {   // _queryhash_subm: centred taps
     x = v.y + kx - (a.ksx - 1) / 2; y = v.z + ky - (a.ksy - 1) / 2; z = v.w + kz - (a.ksz - 1) / 2;
-  } else {                                      // _queryhash_sp with padding 0: taps start at out * stride
-    x = v.y * a.sx + kx; y = v.z * a.sy + ky; z = v.w * a.sz + kz;
+  } else {        // _queryhash_sp: input = out * stride - padding + tap offset
+    x = v.y * a.sx - a.px + tap_offset(kx, a.ksx);
+    y = v.z * a.sy - a.py + tap_offset(ky, a.ksy);
+    z = v.w * a.sz - a.pz + tap_offset(kz, a.ksz);
   }
   int found = -1;
   if (k != a.skip_k && x > -kBias && x < kBias && y > -kBias && y < kBias && z > -kBias && z < kBias) {
@@ -186,9 +231,61 @@ cudaError_t kmap_downsample(int in_nnz, const int *in_coords, int sx, int sy, in
   return cudaGetLastError();
 }
 
+size_t kmap_expand_workspace_bytes(int in_nnz, int k_vol) {
+  const size_t n = (size_t)(in_nnz > 0 ? in_nnz : 1) * (size_t)(k_vol > 0 ? k_vol : 1);
+  size_t sort_tmp = 0, uniq_tmp = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)n);
+  cub::DeviceSelect::Unique(nullptr, uniq_tmp, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int *)nullptr, (int)n);
+  return up256(sort_tmp > uniq_tmp ? sort_tmp : uniq_tmp) + 2 * up256(n * 8) + 1024;
+}
+
+cudaError_t kmap_downsample_expand(int in_nnz, const int *in_coords, int ksx, int ksy, int ksz, int sx, int sy, int sz, int px,
+                                   int py, int pz, const int *lo, const int *hi, int *out_coords, int *out_nnz_dev,
+                                   void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const int k_vol = ksx * ksy * ksz;
+  if (in_nnz < 0 || k_vol < 1 || sx < 1 || sy < 1 || sz < 1 || lo == nullptr || hi == nullptr) return cudaErrorInvalidValue;
+  if ((int64_t)in_nnz * k_vol > 0x7fffffffLL) return cudaErrorInvalidValue;
+  if (in_nnz == 0) return cudaMemsetAsync(out_nnz_dev, 0, sizeof(int), stream);
+  const int n = in_nnz * k_vol;
+  size_t sort_tmp = 0, uniq_tmp = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (unsigned long long *)nullptr, (unsigned long long *)nullptr, n);
+  cub::DeviceSelect::Unique(nullptr, uniq_tmp, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int *)nullptr, n);
+  const size_t tmp = up256(sort_tmp > uniq_tmp ? sort_tmp : uniq_tmp);
+  if (workspace == nullptr || workspace_bytes < tmp + 2 * up256((size_t)n * 8)) return cudaErrorInvalidValue;
+  char *w = static_cast<char *>(workspace);
+  unsigned long long *k0 = reinterpret_cast<unsigned long long *>(w + tmp);
+  unsigned long long *k1 = reinterpret_cast<unsigned long long *>(w + tmp + up256((size_t)n * 8));
+  ExpandArgs a;
+  a.in_nnz = in_nnz; a.ksx = ksx; a.ksy = ksy; a.ksz = ksz; a.k_vol = k_vol; a.sx = sx; a.sy = sy; a.sz = sz;
+  a.px = px; a.py = py; a.pz = pz;
+  for (int d = 0; d < 3; d++) {   // keys hold 16 biased bits per axis
+    a.lo[d] = lo[d] > -kBias + 1 ? lo[d] : -kBias + 1;
+    a.hi[d] = hi[d] < kBias - 1 ? hi[d] : kBias - 1;
+  }
+  a.in_coords = in_coords; a.keys = k0;
+  const int blocks = (n + 255) / 256;
+  expand_keys_kernel<<<blocks, 256, 0, stream>>>(a);
+  size_t t = sort_tmp;
+  cudaError_t e = cub::DeviceRadixSort::SortKeys(w, t, k0, k1, n, 0, 64, stream);   // batch -> x -> y -> z, empty key last
+  if (e != cudaSuccess) return e;
+  t = uniq_tmp;
+  if ((e = cub::DeviceSelect::Unique(w, t, k1, k0, out_nnz_dev, n, stream)) != cudaSuccess) return e;
+  drop_empty_key_kernel<<<1, 32, 0, stream>>>(out_nnz_dev, k0);
+  unpack_keys_kernel<<<blocks, 256, 0, stream>>>(out_nnz_dev, k0, out_coords);
+  return cudaGetLastError();
+}
+
 cudaError_t kmap_build(int in_nnz, const int *in_coords, int out_nnz, const int *out_coords, int ksx, int ksy, int ksz, int sx,
                        int sy, int sz, int q, int skip_mid, int *imap, int *omap, int *knnz, int *kpos, int *qkpos,
                        void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return kmap_build_ex(in_nnz, in_coords, out_nnz, out_coords, ksx, ksy, ksz, sx, sy, sz, 0, 0, 0,
+                       (sx == 1 && sy == 1 && sz == 1) ? 1 : 0, q, skip_mid, imap, omap, knnz, kpos, qkpos, workspace,
+                       workspace_bytes, stream);
+}
+
+cudaError_t kmap_build_ex(int in_nnz, const int *in_coords, int out_nnz, const int *out_coords, int ksx, int ksy, int ksz, int sx,
+                          int sy, int sz, int px, int py, int pz, int subm, int q, int skip_mid, int *imap, int *omap, int *knnz,
+                          int *kpos, int *qkpos, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
   const int k_vol = ksx * ksy * ksz;
   if (in_nnz < 0 || out_nnz < 0 || k_vol < 1 || sx < 1 || sy < 1 || sz < 1 || q < 1) return cudaErrorInvalidValue;
   if ((int64_t)k_vol * out_nnz > 0x7fffffffLL) return cudaErrorInvalidValue;
@@ -213,6 +310,7 @@ cudaError_t kmap_build(int in_nnz, const int *in_coords, int out_nnz, const int 
     // centre tap (k_vol / 2 for odd volumes, 0 otherwise: src/cuda/spconv_cuda.cu:35) left to spconv's separate_mid
     a.skip_k = skip_mid ? ((k_vol % 2 == 1) ? k_vol / 2 : 0) : -1;
     a.out_nnz = out_nnz; a.ksx = ksx; a.ksy = ksy; a.ksz = ksz; a.k_vol = k_vol; a.sx = sx; a.sy = sy; a.sz = sz;
+    a.px = px; a.py = py; a.pz = pz; a.subm = subm;
     a.out_coords = out_coords; a.mask = tsize - 1; a.tkeys = tkeys; a.tval = tval; a.hit = hit; a.flag = flag;
     const int blocks = (int)((cells + 255) / 256);
     query_kernel<<<blocks, 256, 0, stream>>>(a);

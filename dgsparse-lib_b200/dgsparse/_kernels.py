@@ -84,13 +84,16 @@ def sddmm_csr(rowptr, col, D1, D2, mean=False, E=None):
     return out
 
 
-def sddmm_coo(row, col, D1, D2):
-    """[nnz] like the reference torch face (src/cuda/spmm_cuda.cu:314)."""
-    require_cuda(row, col, D1, D2)
+def sddmm_coo(row, col, D1, D2, out=None):
+    """[nnz] like the reference torch face (src/cuda/spmm_cuda.cu:314).  out: optional preallocated fp32 [nnz]."""
+    require_cuda(row, col, D1, D2, out)
     row, col, D1, D2 = _i32c(row, "row"), _i32c(col, "col"), _f32c(D1, "D1"), _f32c(D2, "D2")
     K, nnz = D1.size(1), col.numel()
     with torch.cuda.device(D1.device):
-        out = torch.zeros((nnz,), dtype=torch.float32, device=D1.device)
+        if out is None:
+            out = torch.zeros((nnz,), dtype=torch.float32, device=D1.device)
+        elif out.dtype != torch.float32 or out.numel() != nnz or not out.is_contiguous():
+            raise TypeError("out must be a contiguous float32 tensor with nnz elements")
         if nnz:
             check(lib.dgs_sddmm_coo(K, nnz, ptr(row), ptr(col), ptr(D1), D1.stride(0), ptr(D2), D2.stride(0),
                                     ptr(out), stream_of(D1)), "dgs_sddmm_coo")

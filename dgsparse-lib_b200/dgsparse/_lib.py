@@ -40,6 +40,11 @@ SIGNATURES = {
     "dgs_kmap_downsample": (_i32, [_i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "dgs_kmap_build": (_i32, [_i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
                               _vp, _sz, _vp]),
+    "dgs_kmap_expand_workspace_bytes": (_sz, [_i32, _i32]),
+    "dgs_kmap_downsample_expand": (_i32, [_i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
+                                          _vp, _sz, _vp]),
+    "dgs_kmap_build_ex": (_i32, [_i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dgs_ipc_export": (_i32, [_vp, _vp, ctypes.POINTER(_i64)]),
     "dgs_ipc_open": (_i32, [_vp, ctypes.POINTER(_vp)]),
     "dgs_ipc_close": (_i32, [_vp]),

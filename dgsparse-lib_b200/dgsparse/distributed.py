@@ -131,6 +131,38 @@ def nnz_chunks(nnz: int, world: int):
     return chunk, [(min(nnz, r * chunk), min(nnz, (r + 1) * chunk)) for r in range(world)]
 
 
+class EdgeShardedSDDMM:
+    """SDDMM across the GPUs of one box by splitting the EDGE stream: the pattern and both dense
+    operands are replicated, rank r computes the dots of edges [r*chunk, (r+1)*chunk) with the single-GPU kernel (COO
+    form: the rows of a slice come from the expanded row array, so no rank searches the whole rowptr), and one NCCL
+    all-gather of the [chunk] result slices (4 B per edge) gives every rank the full [1, nnz] output.  Every dot is
+    computed by exactly one rank with the single-GPU arithmetic, so the result is bit-identical to one GPU — unlike
+    the alternative split along K, whose all-reduce changes the summation order."""
+
+    def __init__(self, rowptr, col, group=None):
+        from . import _kernels
+        self._K = _kernels
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.M, self.nnz = rowptr.numel() - 1, col.numel()
+        self.chunk, spans = nnz_chunks(self.nnz, self.world)
+        self.lo, self.hi = spans[self.rank]
+        deg = (rowptr[1:] - rowptr[:-1]).long()
+        row = torch.repeat_interleave(torch.arange(self.M, dtype=torch.int32, device=col.device), deg)
+        self.row = row[self.lo:self.hi].contiguous()
+        self.col = col[self.lo:self.hi].contiguous()
+        self.out = torch.zeros(self.chunk * self.world, dtype=torch.float32, device=col.device)
+
+    def __call__(self, D1: torch.Tensor, D2: torch.Tensor) -> torch.Tensor:
+        """D1 [M, K], D2 [ncols, K] fp32, replicated.  Returns [1, nnz] (the torch-face shape) on every rank."""
+        mine = self.out[self.rank * self.chunk:(self.rank + 1) * self.chunk]
+        self._K.sddmm_coo(self.row, self.col, D1, D2, out=mine[:self.hi - self.lo])
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.out, mine, group=self.group)   # in place: the slice is already at its offset
+        return self.out[:self.nnz].reshape(1, self.nnz)
+
+
 class HostColumnShardedSpMM:
     """The column-sharded SpMM for HOST-resident operands (the multi-GPU counterpart of dgs_spmm_csr_host).
 

@@ -5,12 +5,14 @@ whose output is a dense input-major table; this module exposes the well-defined 
 (dgs_kmap_downsample / dgs_kmap_build of include/dgsparse_b200.h):
 
     km = build_kernel_map(in_coords, kernel_size=3, stride=1)            # submanifold layer
+    km = build_kernel_map(in_coords, kernel_size=3, stride=2, padding=1) # general strided layer (expand branch)
     out = torch.ops.dgsparse_spconv.spconv(feats, W, km.kpos, km.qkpos, km.in_map, km.out_map,
                                            km.out_nnz, km.sum_nnz, km.separate_mid, True)
 
 in_coords: int32 [n, 4] = (batch, x, y, z) on a CUDA device.  Deterministic: pairs are grouped by kernel tap
 (tap = (kx*ks + ky)*ks + kz) and ordered by output index inside a tap.
 """
+import ctypes
 from dataclasses import dataclass
 
 import torch
@@ -53,18 +55,53 @@ def downsample_coords(in_coords: torch.Tensor, stride) -> torch.Tensor:
         return out[: int(cnt.item())]
 
 
-def build_kernel_map(in_coords: torch.Tensor, kernel_size=3, stride=1, separate_mid: bool = False, q: int = 128) -> KernelMap:
-    """stride 1: submanifold layer (out_coords = in_coords, centred taps); stride > 1: down-sampling layer
-    (out_coords = downsample_coords(in_coords, stride), taps out*stride + [0, kernel_size))."""
+def expand_coords(in_coords: torch.Tensor, kernel_size, stride, padding=0, min_coord=None, max_coord=None) -> torch.Tensor:
+    """Output voxels of a general strided layer — the coordsDownsampleExpand branch, src/cuda/sparse_mapping.cu:98-137:
+    sorted unique of (in - off(tap) + padding) / stride over every (input, tap) whose division is exact and whose result
+    lies in [min_coord, max_coord] (output resolution; None = unbounded)."""
+    require_cuda(in_coords)
+    if in_coords.dtype != torch.int32 or in_coords.dim() != 2 or in_coords.size(1) != 4:
+        raise TypeError("in_coords must be int32 [n, 4] = (batch, x, y, z)")
+    c = in_coords.contiguous()
+    n = c.size(0)
+    ks, st, pd = _triple(kernel_size), _triple(stride), _triple(padding)
+    k_vol = ks[0] * ks[1] * ks[2]
+    lo = (ctypes.c_int * 3)(*(_triple(min_coord) if min_coord is not None else (-(1 << 30),) * 3))
+    hi = (ctypes.c_int * 3)(*(_triple(max_coord) if max_coord is not None else ((1 << 30),) * 3))
+    with torch.cuda.device(c.device):
+        out = torch.empty((max(n * k_vol, 1), 4), dtype=torch.int32, device=c.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=c.device)
+        ws = torch.empty(lib.dgs_kmap_expand_workspace_bytes(n, k_vol), dtype=torch.uint8, device=c.device)
+        check(lib.dgs_kmap_downsample_expand(n, ptr(c), ks[0], ks[1], ks[2], st[0], st[1], st[2], pd[0], pd[1], pd[2],
+                                             ctypes.cast(lo, ctypes.c_void_p), ctypes.cast(hi, ctypes.c_void_p), ptr(out),
+                                             ptr(cnt), ptr(ws), ws.numel(), stream_of(c)), "dgs_kmap_downsample_expand")
+        return out[: int(cnt.item())].clone()
+
+
+def build_kernel_map(in_coords: torch.Tensor, kernel_size=3, stride=1, separate_mid: bool = False, q: int = 128,
+                     padding=None, min_coord=None, max_coord=None) -> KernelMap:
+    """Three kinds of layer, chosen as sparse_mapping does (src/cuda/sparse_mapping.cu:60-137):
+      * stride 1, padding None: submanifold layer — out_coords = in_coords, centred taps (the `separate_mid` branch);
+      * padding None or 0 and every stride equal to 1 or the kernel size: plain down-sampling — out_coords =
+        downsample_coords(in_coords, stride), taps out*stride + off(tap);
+      * anything else (e.g. kernel 3, stride 2, padding 1): out_coords = expand_coords(...), the set of voxels whose
+        receptive field out*stride - padding + off(tap) holds an input, optionally clipped to [min_coord, max_coord]."""
     require_cuda(in_coords)
     ks, st = _triple(kernel_size), _triple(stride)
+    pd = _triple(padding) if padding is not None else (0, 0, 0)
     c = in_coords.contiguous()
     if c.dtype != torch.int32 or c.dim() != 2 or c.size(1) != 4:
         raise TypeError("in_coords must be int32 [n, 4] = (batch, x, y, z)")
-    sub = st == (1, 1, 1)
+    sub = st == (1, 1, 1) and padding is None
     if separate_mid and not sub:
-        raise ValueError("separate_mid needs a submanifold layer (stride 1)")
-    out_coords = c if sub else downsample_coords(c, st)
+        raise ValueError("separate_mid needs a submanifold layer (stride 1, padding None)")
+    plain = pd == (0, 0, 0) and min_coord is None and max_coord is None and all(s in (1, k) for s, k in zip(st, ks))
+    if sub:
+        out_coords = c
+    elif plain:
+        out_coords = downsample_coords(c, st)
+    else:
+        out_coords = expand_coords(c, ks, st, pd, min_coord, max_coord)
     n_in, n_out = c.size(0), out_coords.size(0)
     k_vol = ks[0] * ks[1] * ks[2]
     with torch.cuda.device(c.device):
@@ -75,9 +112,9 @@ def build_kernel_map(in_coords: torch.Tensor, kernel_size=3, stride=1, separate_
         kpos = torch.zeros(k_vol + 1, dtype=torch.int32, device=dev)
         qkpos = torch.zeros(k_vol + 1, dtype=torch.int32, device=dev)
         ws = torch.empty(lib.dgs_kmap_workspace_bytes(n_in, n_out, k_vol), dtype=torch.uint8, device=dev)
-        check(lib.dgs_kmap_build(n_in, ptr(c), n_out, ptr(out_coords), ks[0], ks[1], ks[2], st[0], st[1], st[2], q,
-                                 int(separate_mid), ptr(imap), ptr(omap), ptr(knnz), ptr(kpos), ptr(qkpos), ptr(ws),
-                                 ws.numel(), stream_of(c)), "dgs_kmap_build")
+        check(lib.dgs_kmap_build_ex(n_in, ptr(c), n_out, ptr(out_coords), ks[0], ks[1], ks[2], st[0], st[1], st[2],
+                                    pd[0], pd[1], pd[2], int(sub), q, int(separate_mid), ptr(imap), ptr(omap), ptr(knnz),
+                                    ptr(kpos), ptr(qkpos), ptr(ws), ws.numel(), stream_of(c)), "dgs_kmap_build_ex")
         ends = torch.stack([kpos[-1], qkpos[-1]]).cpu()
     pairs, sum_nnz = int(ends[0]), int(ends[1])
     return KernelMap(out_coords, imap[:pairs], omap[:pairs], knnz, kpos, qkpos, n_out, sum_nnz, separate_mid)

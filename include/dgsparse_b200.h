@@ -112,6 +112,24 @@ int dgs_kmap_build(int in_nnz, const int *in_coords, int out_nnz, const int *out
                    int sx, int sy, int sz, int q, int skip_mid, int *imap, int *omap, int *knnz, int *kpos, int *qkpos,
                    void *workspace, size_t workspace_bytes, void *stream);
 
+/* General layers (stride neither 1 nor the kernel size, padding, output bounds): the coordsDownsampleExpand branch of
+ * the reference (src/cuda/sparse_mapping.cu:98-137, include/cuda/sparse_mapping.cuh:326-401).
+ *   dgs_kmap_downsample_expand: out_coords = sorted unique of the voxels (in - off(tap) + padding) / stride over all
+ *                        (input, tap) whose division is exact and whose result lies in [lo, hi] (3 HOST ints each,
+ *                        output resolution); off(k) = k - (ks-1)/2 (+1 for odd ks > 1), the reference's tap decode.
+ *                        Capacity in_nnz * k_vol rows; count to the DEVICE int *out_nnz_dev.  Padding is per axis (the
+ *                        reference reads padding[0] for all three axes in this kernel and padding[0..2] in the query).
+ *   dgs_kmap_build_ex:   dgs_kmap_build with padding: subm != 0 -> input = out + (tap - (ks-1)/2); otherwise
+ *                        input = out * stride - padding + off(tap) (_queryhash_sp, :141-220).  dgs_kmap_build is
+ *                        dgs_kmap_build_ex with padding 0 and subm = (all strides 1). */
+size_t dgs_kmap_expand_workspace_bytes(int in_nnz, int k_vol);
+int dgs_kmap_downsample_expand(int in_nnz, const int *in_coords, int ksx, int ksy, int ksz, int sx, int sy, int sz, int px,
+                               int py, int pz, const int *lo, const int *hi, int *out_coords, int *out_nnz_dev,
+                               void *workspace, size_t workspace_bytes, void *stream);
+int dgs_kmap_build_ex(int in_nnz, const int *in_coords, int out_nnz, const int *out_coords, int ksx, int ksy, int ksz,
+                      int sx, int sy, int sz, int px, int py, int pz, int subm, int q, int skip_mid, int *imap, int *omap,
+                      int *knnz, int *kpos, int *qkpos, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Peer memory for the fused column-shard epilogue: export a device allocation to the other ranks of
  * the box (CUDA IPC), open theirs; the opened base + offset is passed in dst[] of dgs_spmm_csr_multi. */
 int dgs_ipc_export(const void *dptr, void *handle64, int64_t *offset);

@@ -64,6 +64,22 @@ def main():
     assert flag.item() == 1
     hop.close()
     dist.barrier()
+    # edge-sharded SDDMM: every rank ends up with the single-GPU result, bit for bit
+    from dgsparse.distributed import EdgeShardedSDDMM
+    for Kd in (32, 256):
+        D1 = torch.from_numpy(graphs.uniform(M * Kd, 5, -1, 1).reshape(M, Kd)).to(dev)
+        D2 = torch.from_numpy(graphs.uniform(M * Kd, 6, -1, 1).reshape(M, Kd)).to(dev)
+        want = K.sddmm_csr(rp, cc, D1, D2)
+        sd = EdgeShardedSDDMM(rp, cc)
+        for it in range(2):
+            got = sd(D1, D2)
+        torch.cuda.synchronize()
+        flag = torch.tensor([int(torch.equal(got, want))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"edge-sharded sddmm K={Kd} identical={bool(flag.item())}", flush=True)
+        assert flag.item() == 1, Kd
+    dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
         print("MGPU_OK", flush=True)

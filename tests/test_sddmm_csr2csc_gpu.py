@@ -150,3 +150,19 @@ def test_edge_softmax(graphs):
         if e > s:
             x = np.exp(v[s:e] - v[s:e].max(0))
             assert np.allclose(out[s:e], x / x.sum(0), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("Kd", [16, 64, 256])
+def test_edge_sharded_sddmm_single_rank_matches_csr(K, graphs, Kd):
+    """dgsparse.distributed.EdgeShardedSDDMM at world 1 (the 2-rank run is tests/test_multigpu_gpu.py): the COO
+    slice kernel must reproduce the CSR kernel bit for bit, empty rows and hub rows included."""
+    from dgsparse.distributed import EdgeShardedSDDMM
+    M = 3000
+    rowptr, col = graphs.random_csr(M, M, 70000, 9, empty_frac=0.3, hub=2)
+    D1 = dev(graphs.uniform(M * Kd, 3, -1, 1).reshape(M, Kd))
+    D2 = dev(graphs.uniform(M * Kd, 4, -1, 1).reshape(M, Kd))
+    rp, cc = dev(rowptr), dev(col)
+    op = EdgeShardedSDDMM(rp, cc)
+    got = op(D1, D2)
+    assert tuple(got.shape) == (1, col.size)
+    assert torch.equal(got, K.sddmm_csr(rp, cc, D1, D2))
