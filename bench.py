@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="reddit64", choices=["reddit64", "products128", "arxiv256"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debug only; default 1.0)")
-    ap.add_argument("--mode", default=None, choices=[None, "peer", "nccl"], help="N>1 exchange (default: peer)")
+    ap.add_argument("--mode", default=None, choices=[None, "mcast", "peer", "nccl"], help="N>1 exchange (default: mcast, falling back to peer, then nccl)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")

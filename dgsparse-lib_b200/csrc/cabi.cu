@@ -137,6 +137,17 @@ int dgs_spmm_csr_multi(int M, int N, int64_t nnz, const int *rowptr, const int *
   return ok_or(dgs::spmm_csr(p, workspace, workspace_bytes, (cudaStream_t)stream), "dgs_spmm_csr_multi");
 }
 
+int dgs_spmm_csr_mcast(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
+                       int64_t ldb, float *mc_dst, int64_t ldc, int reduce, int compute, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+  if (mc_dst == nullptr) return fail(cudaErrorInvalidValue, "dgs_spmm_csr_mcast(mc_dst)");
+  dgs::SpmmProblem p;
+  p.M = M; p.N = N; p.nnz = nnz; p.rowptr = rowptr; p.col = col; p.val = val; p.B = B; p.ldb = ldb;
+  p.n_dst = 1; p.mcast = 1; p.dst[0] = mc_dst;
+  p.ldc = ldc; p.reduce = reduce; p.compute = compute;
+  return ok_or(dgs::spmm_csr(p, workspace, workspace_bytes, (cudaStream_t)stream), "dgs_spmm_csr_mcast");
+}
+
 int dgs_spmm_csr(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
                  int64_t ldb, float *C, int64_t ldc, int *E, int64_t lde, int reduce, int compute, void *workspace,
                  size_t workspace_bytes, void *stream) {

@@ -74,6 +74,17 @@ template <int VEC> __device__ __forceinline__ void st_vec_cs(float *p, const flo
   else __stcs(p, s[0]);
 }
 
+// One store to an NVLS multicast address: the NVSwitch replicates it into the same offset of every GPU bound to the
+// multicast object (this one included), so a column-shard epilogue sends each finished row ONCE instead of once per peer.
+template <int VEC> __device__ __forceinline__ void st_vec_multimem(float *p, const float (&s)[VEC]) {
+  if (VEC == 4)
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]) : "memory");
+  else {
+#pragma unroll
+    for (int v = 0; v < VEC; v++) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p + v), "f"(s[v]) : "memory");
+  }
+}
+
 template <int VEC> __device__ __forceinline__ void st_vec_cs(int *p, const int (&s)[VEC]) {
   if (VEC == 4) __stcs(reinterpret_cast<int4 *>(p), make_int4(s[0], s[1], s[2], s[3]));
   else if (VEC == 2) __stcs(reinterpret_cast<int2 *>(p), make_int2(s[0], s[1]));

@@ -159,6 +159,8 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   a.mask = p.mask; a.ldm = p.ldm;
   a.mean = (p.reduce == R_MEAN);
   a.n_dst = p.n_dst;
+  a.mcast = p.mcast;
+  if (p.mcast && p.n_dst != 1) return cudaErrorInvalidValue;
   for (int d = 0; d < kMaxDst; d++) a.dst[d] = d < p.n_dst ? p.dst[d] : nullptr;
 
   int vec = 1, G = 32;

@@ -15,6 +15,7 @@ struct SpmmProblem {
   const float *B = nullptr;
   int64_t ldb = 0;
   int n_dst = 1;
+  int mcast = 0;                // dst[0] is an NVLS multicast address covering every rank's C (requires n_dst == 1)
   float *dst[8] = {nullptr};    // dst[0] = C; further entries = NVLink peers' C (column-shard epilogue)
   int64_t ldc = 0;
   int *E = nullptr;             // arg column index out (MAX / MIN only)

@@ -43,6 +43,7 @@ struct SpmmArgs {
   int *part_arg;      // same shape, only with ARG
   int *tail_row;      // [num_chunks] row whose tail partial lives in slot 1, or -1
   int n_dst;          // 1 (local C) or the number of column-shard peers
+  int mcast;          // dst[0] is an NVLS multicast address: one multimem.st reaches every rank's C (n_dst == 1)
   float *dst[kMaxDst];
   const int *mask;    // COMP == C_MASK only: arg index tensor E of the forward, [*, ldm]
   int64_t ldm;
@@ -131,8 +132,11 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
 #pragma unroll
         for (int v = 0; v < VEC; v++) o[v] = a.mean ? acc[v] / deg : acc[v];
         const size_t off = (size_t)r * a.ldc + colbase;
-        st_vec_cs<VEC>(a.dst[0] + off, o);
-        for (int d = 1; d < a.n_dst; d++) st_vec_cs<VEC>(a.dst[d] + off, o);   // NVLink peers
+        if (a.mcast) st_vec_multimem<VEC>(a.dst[0] + off, o);                   // NVSwitch multicast: all ranks at once
+        else {
+          st_vec_cs<VEC>(a.dst[0] + off, o);
+          for (int d = 1; d < a.n_dst; d++) st_vec_cs<VEC>(a.dst[d] + off, o);   // NVLink peers
+        }
         if (ARG) st_vec_cs<VEC>(a.E + (size_t)r * a.lde + colbase, arg);
       } else {
         store_partial(0);     // the row began in an earlier segment: head partial
@@ -291,7 +295,8 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
         for (int v = 0; v < FV; v++) acc[v] = acc[v] / deg;
       }
       const size_t off = (size_t)r * a.ldc + c;
-      for (int d = 0; d < a.n_dst; d++) st_vec_cs<FV>(a.dst[d] + off, acc);
+      if (a.mcast) st_vec_multimem<FV>(a.dst[0] + off, acc);
+      else for (int d = 0; d < a.n_dst; d++) st_vec_cs<FV>(a.dst[d] + off, acc);
       if (ARG) st_vec_cs<FV>(a.E + (size_t)r * a.lde + c, arg);
     }
   }
@@ -308,7 +313,8 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
       const int rr = (int)row0 + (__ffs(m) - 1);
       m &= m - 1;
       for (int c = lane; c < a.N; c += 32) {
-        for (int d = 0; d < a.n_dst; d++) a.dst[d][(size_t)rr * a.ldc + c] = 0.0f;
+        if (a.mcast) { const float z[1] = {0.0f}; st_vec_multimem<1>(a.dst[0] + (size_t)rr * a.ldc + c, z); }
+        else for (int d = 0; d < a.n_dst; d++) a.dst[d][(size_t)rr * a.ldc + c] = 0.0f;
         if (ARG) a.E[(size_t)rr * a.lde + c] = -1;
       }
     }

@@ -9,6 +9,10 @@ output panel is then made available on every rank, in one of two ways:
                row-major C[M, n_total] at column offset r*n_local through NVLink-mapped peer pointers
                (CUDA IPC), so the transfer overlaps the remaining row segments; one stream-ordered
                NCCL all-reduce of a single int afterwards is the completion barrier.
+  mode="mcast" (tried first when the ranks share an NVSwitch): the same fused epilogue, but C lives in torch symmetric
+               memory and every finished row segment is stored ONCE to the NVLS multicast address
+               (multimem.st, dgs_spmm_csr_mcast): the switch replicates it into every rank's C, so a rank sends
+               M*n_local*4 bytes per step instead of (world-1) times that.
   mode="nccl"  the baseline: local SpMM, then one ncclAllGather of the [M, n_local] panel into a
                panel-major [world, M, n_local] buffer (panels_to_row_major() permutes when needed).
 
@@ -59,10 +63,21 @@ class ColumnShardedSpMM:
         self.reduce, self.compute = reduce, compute
         dev = col.device
         self.ws = torch.empty(max(256, _lib.lib.dgs_spmm_workspace_bytes(n_local, self.nnz, 0)), dtype=torch.uint8, device=dev)
-        self.C = torch.empty((self.M, self.n_total), dtype=torch.float32, device=dev)
+        self.C = None
         self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._opened = []
-        self.mode = mode or ("peer" if self.world > 1 else "local")
+        self.mode = mode or ("mcast" if self.world > 1 else "local")
+        if self.world > 1 and self.mode == "mcast":
+            try:
+                self._map_multicast(dev)
+            except Exception as e:  # no NVLS / symmetric memory on this box: every rank must agree on the fallback
+                self._mcast_error = str(e)
+                self.mode = "peer"
+            agreed = exchange_objects(self.mode, group)
+            if any(m != "mcast" for m in agreed):
+                self.mode = "peer"
+        if self.C is None or self.mode != "mcast":
+            self.C = torch.empty((self.M, self.n_total), dtype=torch.float32, device=dev)
         if self.world > 1 and self.mode == "peer":
             try:
                 self._map_peers()
@@ -75,6 +90,18 @@ class ColumnShardedSpMM:
         if self.mode == "nccl":
             self.C_local = torch.empty((self.M, n_local), dtype=torch.float32, device=dev)
             self.panels = torch.empty((self.world, self.M, n_local), dtype=torch.float32, device=dev)
+
+    def _map_multicast(self, dev):
+        """C in torch symmetric memory (plumbing: allocation + rendezvous); the kernel only needs the multicast address."""
+        import torch.distributed._symmetric_memory as symm
+        group = self.group if self.group is not None else dist.group.WORLD
+        C = symm.empty((self.M, self.n_total), dtype=torch.float32, device=dev)
+        hdl = symm.rendezvous(C, group)
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if mc == 0:
+            raise RuntimeError("symmetric memory has no multicast mapping on this box")
+        self.C, self._symm = C, hdl
+        self._mc_dst = mc + self.lo * 4
 
     def _map_peers(self):
         L = self._lib
@@ -108,6 +135,12 @@ class ColumnShardedSpMM:
                                      self.reduce, self.compute, ptr(self.ws), self.ws.numel(), stream), "dgs_spmm_csr")
             dist.all_gather_into_tensor(self.panels, self.C_local, group=self.group)
             return self.panels
+        if self.mode == "mcast":
+            L.check(lib.dgs_spmm_csr_mcast(self.M, self.n_local, self.nnz, ptr(self.rowptr), ptr(self.col), ptr(self.values),
+                                           ptr(B_local), B_local.stride(0), self._mc_dst, self.n_total, self.reduce,
+                                           self.compute, ptr(self.ws), self.ws.numel(), stream), "dgs_spmm_csr_mcast")
+            dist.all_reduce(self._flag, group=self.group)   # completion barrier: every rank's multicast stores have landed
+            return self.C
         if self.mode == "local":
             dst = (ctypes.c_void_p * 1)(self.C.data_ptr())
         else:

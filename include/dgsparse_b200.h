@@ -44,6 +44,14 @@ int dgs_spmm_csr_multi(int M, int N, int64_t nnz, const int *rowptr, const int *
                        int64_t ldb, int n_dst, float *const *dst, int64_t ldc, int reduce, int compute, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* The same epilogue through an NVLS MULTICAST address (NVSwitch, sm_90+): mc_dst is the multicast mapping of a buffer
+ * bound on every rank of the box (e.g. the multicast_ptr of a torch symmetric-memory rendezvous) offset to this rank's
+ * column panel; each finished row is sent ONCE with multimem.st and the switch replicates it into every rank's C,
+ * this rank's included.  Same completion rule as dgs_spmm_csr_multi: a stream-ordered barrier across the ranks. */
+int dgs_spmm_csr_mcast(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
+                       int64_t ldb, float *mc_dst, int64_t ldc, int reduce, int compute, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
 /* Masked SpMM of the max/min backward (grad wrt dense), called on the CSC arrays:
  *   out[j, v] = sum_{p in ptr[j]..ptr[j+1]} [E[idx[p], v] == j] * val[p] * G[idx[p], v]
  * Replaces spmm_cuda_with_mask src/cuda/spmm_cuda.cu:255-303 (intended semantics of

@@ -30,12 +30,12 @@ def main():
     B_local = Bf[:, rank * n_local:(rank + 1) * n_local].contiguous()
     for reduce in (L.SUM, L.MAX):
         refr = K.spmm(rp, cc, vv, Bf, reduce, L.MUL)
-        for mode in ("peer", "nccl"):
+        for mode in ("mcast", "peer", "nccl"):
             op = ColumnShardedSpMM(rp, cc, vv, n_local, reduce=reduce, mode=mode)
             for it in range(3):
                 out = op(B_local)
             torch.cuda.synchronize()
-            C = out if op.mode == "peer" else panels_to_row_major(out)
+            C = out if op.mode in ("peer", "mcast") else panels_to_row_major(out)
             ok = torch.equal(C, refr)                              # no reduction across ranks: bit-identical
             flag = torch.tensor([int(ok)], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -44,6 +44,8 @@ def main():
             assert flag.item() == 1, (mode, reduce)
             if mode == "peer" and rank == 0 and op.mode != "peer":
                 print("PEER MAPPING UNAVAILABLE:", getattr(op, "_peer_error", "?"), flush=True)
+            if mode == "mcast" and rank == 0 and op.mode != "mcast":
+                print("MULTICAST UNAVAILABLE:", getattr(op, "_mcast_error", "?"), flush=True)
             dist.barrier()
             op.close()
     # host-resident operands: sliced upload + NVLink all-gather of the CSR, own panel back to the host
