@@ -10,8 +10,8 @@ convention, example/ge-spmm/spmm.cu:213-215), with the achieved HBM GB/s (algori
 
 N>1 (torchrun, one rank per GPU): the feature axis is sharded — every rank holds the replicated CSR and a
 64-column panel of B (total feat = 64*N; N=8 is config 5), computes its panel of C and makes it visible on
-every rank (fused peer-store epilogue over NVLink + a one-int NCCL barrier, or an NCCL allgather when
-peer mapping is unavailable).  Per-GPU work is fixed -> "weak".  value = 2*nnz*64*N / max-over-ranks time.
+every rank (fused NVLS-multicast or peer-store epilogue over NVLink + a one-int NCCL barrier, or an NCCL allgather
+when neither mapping is available).  Per-GPU work is fixed -> "weak".  value = 2*nnz*64*N / max-over-ranks time.
 
 --impl reference: the reference's own CPU implementation of the path (spmm_reference_host from
 oracle/_ref when it was built from /root/reference, else the oracle port) on the host cores, rank 0 only.
@@ -388,7 +388,7 @@ def main():
             dist.all_reduce(tot)
             h2d, d2h = int(tot[0].item()), int(tot[1].item())
             api = ("dgsparse.distributed.HostColumnShardedSpMM: pinned host CSR slice (1/world per rank) + B panel in, "
-                   "NCCL all-gather of col/val over NVLink, fused peer-store SpMM, own C panel out; bytes are whole-job totals")
+                   "NCCL all-gather of col/val over NVLink, fused multicast / peer-store SpMM, own C panel out; bytes are whole-job totals")
         for _ in range(2):
             e2e_step()
         barrier()
