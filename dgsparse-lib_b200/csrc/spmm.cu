@@ -102,12 +102,27 @@ static void pick_geometry(int N, bool can_vec4, int *vec, int *G) {
 }
 
 // Segment length (nnz per lane group).  Depends only on (N, nnz, with_arg, #SMs) so that
-// spmm_workspace_bytes() and the launch agree.  Aim: ~8 segments per resident group (dynamic balance
+// spmm_workspace_bytes() and the launch agree.  Aim: segs_per_group() segments per resident group (dynamic balance
 // through the block scheduler) while the partial workspace stays below kWorkspaceCap.
 static constexpr size_t kWorkspaceCap = 192u << 20;
+// Segments per resident lane group: more segments = finer dynamic balance through the block scheduler, fewer = fewer rows
+// cut by a segment boundary (those are finished by the fix-up kernel, which on N GPUs is an NVLink-ingress burst).
+// Measured on B200 (DGS_SPMM_SEGS sweep): the main kernel does not care (reddit@64 1.573 / 1.568 / 1.567 / 1.570 / 1.575 ms
+// for 8 / 4 / 3 / 2 / 1, products@128 8.95 / 8.93 / 8.95 ms for 8 / 4 / 3) while the fix-up shrinks from 0.018 to 0.013 ms.
+static int segs_per_group() {
+  static int v = 0;
+  if (v == 0) {
+    const char *e = getenv("DGS_SPMM_SEGS");
+    v = e ? atoi(e) : 4;
+    if (v < 1 || v > 64) v = 4;
+  }
+  return v;
+}
+
 static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
   const int64_t resident_groups = (int64_t)device_sm_count() * 3 * (kSpmmThreads / G);
-  int64_t chunk = (nnz + resident_groups * 8 - 1) / (resident_groups * 8);
+  const int spg = segs_per_group();
+  int64_t chunk = (nnz + resident_groups * spg - 1) / (resident_groups * spg);
   if (chunk < 64) chunk = 64;
   if (chunk > 8192) chunk = 8192;
   const size_t per_chunk = (size_t)2 * N * 4 * (with_arg ? 2 : 1) + 4;
