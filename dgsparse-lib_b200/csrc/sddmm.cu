@@ -201,7 +201,9 @@ __global__ void __launch_bounds__(kSdThreads) sddmm_kernel(const SddmmArgs a) {
 // (a fractional evict_last policy on D2, 0.3 .. 0.9 of L2, was measured and changed nothing: 0.198 - 0.205 ms;
 // column-range passes that keep one slice of D2 L2-resident per pass, with the pass's edges compacted by shuffles,
 // were measured too: 0.208 ms for 1 pass, 0.277 / 0.348 / 0.413 ms for 2 / 3 / 4 — the kernel is bound by per-warp
-// issue latency, not by the 909 MB of DRAM traffic, so re-walking the edge list costs more than the misses it saves).
+// issue latency, not by the 909 MB of DRAM traffic, so re-walking the edge list costs more than the misses it saves;
+// FEATURE-axis passes — K/p columns per pass with the full leading dimension, so that a narrower D2 slice stays L2-resident
+// — lose as well: 0.197 ms for 1 pass, 0.242 for 2 x 128 columns, 0.450 for 4 x 64, tools/exp_sddmm_fsplit.py).
 constexpr int kRgNB = 4;          // edges per batch: one per 8-lane group of the copying warp
 constexpr int kRgBPS = 32 / kRgNB; // batches per 32-edge superbatch
 constexpr int kRgMetaBytes = 2 * kRgBPS * 4 + 2 * 32 * 4;   // two superbatches of packed slots + degrees
