@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kSdThreads) sddmm_kernel(const SddmmArgs a) {
     row_start = row_end;
     row_end = __ldg(a.rowptr + r + 1);
     if (row_end <= pos) {
-      r = row_of_nnz(a.rowptr, a.M, pos);
+      r = row_of_nnz_from(a.rowptr, a.M, pos, r);
       row_start = __ldg(a.rowptr + r);
       row_end = __ldg(a.rowptr + r + 1);
     }

@@ -123,7 +123,12 @@ static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
   const int64_t resident_groups = (int64_t)device_sm_count() * 3 * (kSpmmThreads / G);
   const int spg = segs_per_group();
   int64_t chunk = (nnz + resident_groups * spg - 1) / (resident_groups * spg);
-  if (chunk < 64) chunk = 64;
+  // Small matrices (latency regime): one 32-nnz batch per segment spreads them over more SMs; with two or more column
+  // panels (N > 64) the extra cut rows cost more than that buys.  p2p-Gnutella31 / ca-CondMat, us per call, min 32 | 64 | 128:
+  // N=32 26.7 | 34.9 | 55.3 and 20.5 | 22.6 | 34.5;  N=64 24.7 | 29.5 | 41.0 and 20.5 | 22.4 | 28.2;  N=128 35.0 | 32.9 | 43.0
+  // and 30.7 | 26.4 | 32.9.
+  const int min_chunk = (N <= 64) ? kBatch : 2 * kBatch;
+  if (chunk < min_chunk) chunk = min_chunk;
   if (chunk > 8192) chunk = 8192;
   const size_t per_chunk = (size_t)2 * N * 4 * (with_arg ? 2 : 1) + 4;
   const int64_t min_for_ws = (int64_t)(((size_t)nnz * per_chunk + kWorkspaceCap - 1) / kWorkspaceCap);

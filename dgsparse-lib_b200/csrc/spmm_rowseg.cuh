@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
     r += 1;
     row_start = row_end;
     row_end = __ldg(rowptr + r + 1);
-    if (row_end <= pos) {           // run of empty rows: jump
-      r = row_of_nnz(rowptr, a.M, pos);
+    if (row_end <= pos) {           // run of empty rows: jump (galloping search from here)
+      r = row_of_nnz_from(rowptr, a.M, pos, r);
       row_start = __ldg(rowptr + r);
       row_end = __ldg(rowptr + r + 1);
     }
@@ -312,10 +312,14 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
     while (m) {
       const int rr = (int)row0 + (__ffs(m) - 1);
       m &= m - 1;
-      for (int c = lane; c < a.N; c += 32) {
-        if (a.mcast) { const float z[1] = {0.0f}; st_vec_multimem<1>(a.dst[0] + (size_t)rr * a.ldc + c, z); }
-        else for (int d = 0; d < a.n_dst; d++) a.dst[d][(size_t)rr * a.ldc + c] = 0.0f;
-        if (ARG) a.E[(size_t)rr * a.lde + c] = -1;
+      for (int c = lane * FV; c < a.N; c += 32 * FV) {   // FV = 4: 16-byte stores (N % 4 == 0, aligned rows)
+        float z[FV];
+        int m1[FV];
+#pragma unroll
+        for (int v = 0; v < FV; v++) { z[v] = 0.0f; m1[v] = -1; }
+        if (a.mcast) st_vec_multimem<FV>(a.dst[0] + (size_t)rr * a.ldc + c, z);
+        else for (int d = 0; d < a.n_dst; d++) st_vec_cs<FV>(a.dst[d] + (size_t)rr * a.ldc + c, z);
+        if (ARG) st_vec_cs<FV>(a.E + (size_t)rr * a.lde + c, m1);
       }
     }
   }
