@@ -44,12 +44,14 @@ __device__ __forceinline__ int row_of_nnz(const int *__restrict__ rowptr, int M,
   return upper_bound_i32(rowptr, M + 1, p) - 1;
 }
 
-// The same, searching FORWARD from a row r0 known to start at or before p (rowptr[r0] <= p): gallop, then bisect —
-// O(log distance) loads.  Rows advance by a handful at a time inside a segment, so this is 2-4 loads where the full
-// search is log2(M) dependent ones (on p2p-Gnutella31, 74 % empty rows, the full search was most of the kernel).
+// The same, searching FORWARD from a row r0 known to start at or before p (rowptr[r0] <= p): one probe decides between a
+// 32-row window and the rest of the matrix, then ONE bisection loop (the same code shape as the full search — a galloping
+// version with two loops made the SpMM hot loop 20 % slower on a graph that never takes this path).  Rows advance by a
+// handful at a time inside a segment, so this is ~6 loads where the full search is log2(M) dependent ones (on
+// p2p-Gnutella31, 74 % empty rows, the full search was most of the kernel).
 __device__ __forceinline__ int row_of_nnz_from(const int *__restrict__ rowptr, int M, int p, int r0) {
-  int lo = r0 + 1, hi = r0 + 1, step = 1;        // smallest idx in (r0, M] with rowptr[idx] > p
-  while (hi < M && __ldg(rowptr + hi) <= p) { lo = hi + 1; step <<= 1; hi = min(M, hi + step); }
+  int lo = r0 + 1, hi = min(M, r0 + 32);          // smallest idx in (r0, M] with rowptr[idx] > p
+  if (__ldg(rowptr + hi) <= p) { lo = hi + 1; hi = M; }
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     if (__ldg(rowptr + mid) > p) hi = mid; else lo = mid + 1;

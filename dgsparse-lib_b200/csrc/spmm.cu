@@ -127,8 +127,14 @@ static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
   // panels (N > 64) the extra cut rows cost more than that buys.  p2p-Gnutella31 / ca-CondMat, us per call, min 32 | 64 | 128:
   // N=32 26.7 | 34.9 | 55.3 and 20.5 | 22.6 | 34.5;  N=64 24.7 | 29.5 | 41.0 and 20.5 | 22.4 | 28.2;  N=128 35.0 | 32.9 | 43.0
   // and 30.7 | 26.4 | 32.9.
-  const int min_chunk = (N <= 64) ? kBatch : 2 * kBatch;
-  if (chunk < min_chunk) chunk = min_chunk;
+  // Only while the GPU is underfilled, though: once 64-nnz segments give every resident group one (arxiv-like, 1.17 M nnz),
+  // halving them only doubles the per-segment overhead (N=32 0.065 -> 0.088 ms).
+  if (chunk < 2 * kBatch) {
+    const int min_chunk = (N <= 64) ? kBatch : 2 * kBatch;
+    chunk = nnz / resident_groups;
+    if (chunk < min_chunk) chunk = min_chunk;
+    if (chunk > 2 * kBatch) chunk = 2 * kBatch;
+  }
   if (chunk > 8192) chunk = 8192;
   const size_t per_chunk = (size_t)2 * N * 4 * (with_arg ? 2 : 1) + 4;
   const int64_t min_for_ws = (int64_t)(((size_t)nnz * per_chunk + kWorkspaceCap - 1) / kWorkspaceCap);

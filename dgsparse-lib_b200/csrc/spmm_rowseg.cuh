@@ -271,21 +271,33 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
       int arg[FV];
       ld_vec<FV>(acc, a.part_val + ((size_t)g * 2 + 1) * a.N + c);
       if (ARG) ld_ivec<FV>(arg, a.part_arg + ((size_t)g * 2 + 1) * a.N + c);
-      for (int gg = g + 1; gg <= g_last; gg++) {
-        float x[FV];
-        int xa[FV];
-        ld_vec<FV>(x, a.part_val + ((size_t)gg * 2) * a.N + c);
-        if (ARG) ld_ivec<FV>(xa, a.part_arg + ((size_t)gg * 2) * a.N + c);
+      // A hub row spans many segments (arxiv-like, 64-nnz segments: 200): fetch the partials kFoldU at a time (independent
+      // loads), fold them strictly in segment order.  One at a time this loop was a 50 us dependent-load chain.
+      constexpr int kFoldU = 8;
+      for (int g0 = g + 1; g0 <= g_last; g0 += kFoldU) {
+        float x[kFoldU][FV];
+        int xa[kFoldU][FV];
 #pragma unroll
-        for (int v = 0; v < FV; v++) {
-          if (RED == R_MAX) {
-            if (ARG) { if (acc[v] < x[v]) arg[v] = xa[v]; }
-            acc[v] = (acc[v] < x[v]) ? x[v] : acc[v];
-          } else if (RED == R_MIN) {
-            if (ARG) { if (acc[v] > x[v]) arg[v] = xa[v]; }
-            acc[v] = (acc[v] < x[v]) ? acc[v] : x[v];
-          } else {
-            acc[v] += x[v];
+        for (int u = 0; u < kFoldU; u++) {
+          const int gg = min(g0 + u, g_last);
+          ld_vec<FV>(x[u], a.part_val + ((size_t)gg * 2) * a.N + c);
+          if (ARG) ld_ivec<FV>(xa[u], a.part_arg + ((size_t)gg * 2) * a.N + c);
+        }
+#pragma unroll
+        for (int u = 0; u < kFoldU; u++) {
+          if (g0 + u <= g_last) {
+#pragma unroll
+            for (int v = 0; v < FV; v++) {
+              if (RED == R_MAX) {
+                if (ARG) { if (acc[v] < x[u][v]) arg[v] = xa[u][v]; }
+                acc[v] = (acc[v] < x[u][v]) ? x[u][v] : acc[v];
+              } else if (RED == R_MIN) {
+                if (ARG) { if (acc[v] > x[u][v]) arg[v] = xa[u][v]; }
+                acc[v] = (acc[v] < x[u][v]) ? acc[v] : x[u][v];
+              } else {
+                acc[v] += x[u][v];
+              }
+            }
           }
         }
       }
