@@ -37,7 +37,7 @@ def main():
         b.record()
         torch.cuda.synchronize()
         print(f"{name} spmm N={N}: {a.elapsed_time(b) / (reps * 20) * 1e3:.1f} us per call", flush=True)
-    for Kd in (32, 64):
+    for Kd in (32, 64, 128, 256, 512):
         D1, D2 = torch.rand(M, Kd, device="cuda"), torch.rand(M, Kd, device="cuda")
         out = torch.empty(nnz, device="cuda")
         f = lambda: L.lib.dgs_sddmm_csr(M, Kd, nnz, rp.data_ptr(), cc.data_ptr(), D1.data_ptr(), Kd, D2.data_ptr(), Kd, None, 0,
