@@ -276,8 +276,8 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
       ld_vec<FV>(acc, a.part_val + ((size_t)g * 2 + 1) * a.N + c);
       if (ARG) ld_ivec<FV>(arg, a.part_arg + ((size_t)g * 2 + 1) * a.N + c);
       // A hub row spans many segments (arxiv-like, 64-nnz segments: 200): fetch the partials kFoldU at a time (independent
-      // loads), fold them strictly in segment order.  One at a time this loop was a 50 us dependent-load chain.
-      constexpr int kFoldU = 8;
+      // loads, 8 or 16 in flight), fold them strictly in segment order.  One at a time this loop was a 50 us dependent-load chain.
+      constexpr int kFoldU = ARG ? 8 : 16;
       for (int g0 = g + 1; g0 <= g_last; g0 += kFoldU) {
         float x[kFoldU][FV];
         int xa[kFoldU][FV];
