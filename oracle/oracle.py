@@ -35,6 +35,13 @@ def build(force=False):
     if os.path.exists("/root/reference/src/ge-spmm/gespmm.cc") and (
             force or not os.path.exists(_REF_CUDA_SO)):
         subprocess.check_call(["make", "-C", _HERE, "-s", "refcuda"])
+    # the reference's own example drivers linked against OUR library (tests/test_reference_drivers_gpu.py)
+    ours = os.path.join(os.path.dirname(_HERE), "dgsparse-lib_b200", "lib", "libdgsparse_b200.so")
+    drv = os.path.join(_HERE, "_ref", "spmm_example.out")
+    if os.path.exists("/root/reference/example/ge-spmm/spmm.cu") and os.path.exists(ours) and (
+            force or not os.path.exists(drv) or os.path.getmtime(drv) < os.path.getmtime(
+                os.path.join(os.path.dirname(_HERE), "include", "dgsparse.h"))):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "refdrivers"])
 
 
 def _p(a, typ):

@@ -1,0 +1,62 @@
+"""GPU drop-in proof of the dgsparse.h C ABI: the REFERENCE'S OWN self-checking example drivers — example/ge-spmm/spmm.cu
+(every gespmmCsrSpMM algorithm, :171-216) and example/sddmm/sddmm.cu (sddmm_cuda_csr, :167-195) — compiled UNMODIFIED
+where they lie under /root/reference and linked against OUR libdgsparse_b200.so instead of the reference's libgespmm.a /
+libsddmm.a (oracle/Makefile target `refdrivers`; the binaries travel in oracle/_ref/).  Each driver compares every output
+element with spmm_reference_host / sddmm_reference_host (example/util/sp_util.hpp:62-131) and prints its "Report" line
+only when that check passed.  Skipped when the binaries were not built (reference tree absent at build time)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def write_mtx(path, rowptr, col, shape):
+    """The fixture CSR as a MatrixMarket `coordinate pattern general` file (what read_mtx_file, sp_util.hpp:171-248, reads)."""
+    rows = np.repeat(np.arange(shape[0]), np.diff(rowptr))
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate pattern general\n")
+        f.write(f"{shape[0]} {shape[1]} {col.size}\n")
+        np.savetxt(f, np.stack([rows + 1, col.astype(np.int64) + 1], 1), fmt="%d")
+
+
+def run_driver(name, mtx, width):
+    exe = os.path.join(REF_DIR, name)
+    if not os.path.exists(exe):
+        pytest.skip(f"oracle/_ref/{name} not built (make -C oracle refdrivers needs /root/reference)")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = "/usr/local/cuda/lib64:" + env.get("LD_LIBRARY_PATH", "")
+    r = subprocess.run([exe, mtx, str(width)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+@pytest.fixture(scope="module")
+def gnutella_mtx(tmp_path_factory, graphs):
+    rowptr, col, shape = graphs.load_fixture("p2p-Gnutella31")
+    p = str(tmp_path_factory.mktemp("mtx") / "p2p-Gnutella31.mtx")
+    write_mtx(p, rowptr, col, shape)
+    return p, shape, int(col.size)
+
+
+@pytest.mark.parametrize("N", [32])       # configs[0] of BASELINE.json (feat = 32); one width keeps the run short: a driver run is ~45 s
+def test_reference_spmm_example_passes_on_our_library(gnutella_mtx, N):
+    mtx, shape, nnz = gnutella_mtx
+    out = run_driver("spmm_example.out", mtx, N)
+    assert f"Finish reading matrix {shape[0]} rows, {shape[1]} columns, {nnz} nnz" in out
+    assert "Wrong result" not in out
+    # six algorithms (example/ge-spmm/spmm.cu:172-175), each reported only after its element-wise check passed
+    reports = [l for l in out.splitlines() if l.startswith("[GE-SpMM][Alg:")]
+    assert len(reports) == 6, out[-3000:]
+
+
+@pytest.mark.parametrize("K", [64])
+def test_reference_sddmm_example_passes_on_our_library(gnutella_mtx, K):
+    mtx, shape, nnz = gnutella_mtx
+    out = run_driver("sddmm_example.out", mtx, K)
+    assert "Wrong result" not in out
+    assert any(l.startswith("[SDDMM] Report") for l in out.splitlines()), out[-3000:]
