@@ -108,7 +108,9 @@ def test_csr2csc_bit_exact_vs_scipy_golden(K, graphs, name):
     assert np.array_equal(v2.cpu().numpy(), val[z["perm"]])
 
 
-@pytest.mark.parametrize("shape", [(1, 1, 1), (50, 70000, 4000), (70000, 50, 300000), (5000, 5000, 0), (3000, 300, 200000)])
+# (20, 3000000, 50000): 22 key bits = three radix passes (first / middle / last kernels); 70000 columns = two; 50 = one
+@pytest.mark.parametrize("shape", [(1, 1, 1), (50, 70000, 4000), (70000, 50, 300000), (5000, 5000, 0), (3000, 300, 200000),
+                                   (20, 3000000, 50000), (2000, 600000, 150000)])
 def test_csr2csc_shapes(K, oracle, graphs, shape):
     M, Kc, nnz = shape
     if nnz == 0:
