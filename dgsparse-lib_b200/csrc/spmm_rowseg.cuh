@@ -92,6 +92,9 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
   const int grp = threadIdx.x / G;
   const int gl = threadIdx.x % G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (((threadIdx.x & 31) / G) * G));
+  // Programmatic dependent launch: the fix-up grid may start now; its first half (the zero rows of empty rows) touches
+  // nothing this kernel reads or writes, its second half waits for this grid (griddepcontrol.wait).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int chunk_id = blockIdx.x * GPB + grp;
   if (chunk_id >= a.num_chunks) return;
 
@@ -262,6 +265,34 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
 template <int RED, bool ARG, int FV>
 __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // ---- part 1 (independent of the SpMM grid, may overlap it under programmatic dependent launch) ----
+  // empty rows: one warp scans 32 rows, then writes the zero rows cooperatively
+  {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = t >> 5;
+  const int64_t row0 = warp * 32;
+  if (row0 < a.M) {
+    const int row = (int)row0 + lane;
+    bool empty = false;
+    if (row < a.M) empty = __ldg(a.rowptr + row) == __ldg(a.rowptr + row + 1);
+    unsigned m = __ballot_sync(0xffffffffu, empty);
+    while (m) {
+      const int rr = (int)row0 + (__ffs(m) - 1);
+      m &= m - 1;
+      for (int c = lane * FV; c < a.N; c += 32 * FV) {   // FV = 4: 16-byte stores (N % 4 == 0, aligned rows)
+        float z[FV];
+        int m1[FV];
+#pragma unroll
+        for (int v = 0; v < FV; v++) { z[v] = 0.0f; m1[v] = -1; }
+        if (a.mcast) st_vec_multimem<FV>(a.dst[0] + (size_t)rr * a.ldc + c, z);
+        else for (int d = 0; d < a.n_dst; d++) st_vec_cs<FV>(a.dst[d] + (size_t)rr * a.ldc + c, z);
+        if (ARG) st_vec_cs<FV>(a.E + (size_t)rr * a.lde + c, m1);
+      }
+    }
+  }
+  }
+  // ---- part 2: the partials of the SpMM grid must be complete and visible ----
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int nq = a.N / FV;                      // column groups per row
   const int64_t n_fold = (int64_t)a.num_chunks * nq;
   if (t < n_fold) {
@@ -314,29 +345,6 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
       if (a.mcast) st_vec_multimem<FV>(a.dst[0] + off, acc);
       else for (int d = 0; d < a.n_dst; d++) st_vec_cs<FV>(a.dst[d] + off, acc);
       if (ARG) st_vec_cs<FV>(a.E + (size_t)r * a.lde + c, arg);
-    }
-  }
-  // empty rows: one warp scans 32 rows, then writes the zero rows cooperatively
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = t >> 5;
-  const int64_t row0 = warp * 32;
-  if (row0 < a.M) {
-    const int row = (int)row0 + lane;
-    bool empty = false;
-    if (row < a.M) empty = __ldg(a.rowptr + row) == __ldg(a.rowptr + row + 1);
-    unsigned m = __ballot_sync(0xffffffffu, empty);
-    while (m) {
-      const int rr = (int)row0 + (__ffs(m) - 1);
-      m &= m - 1;
-      for (int c = lane * FV; c < a.N; c += 32 * FV) {   // FV = 4: 16-byte stores (N % 4 == 0, aligned rows)
-        float z[FV];
-        int m1[FV];
-#pragma unroll
-        for (int v = 0; v < FV; v++) { z[v] = 0.0f; m1[v] = -1; }
-        if (a.mcast) st_vec_multimem<FV>(a.dst[0] + (size_t)rr * a.ldc + c, z);
-        else for (int d = 0; d < a.n_dst; d++) st_vec_cs<FV>(a.dst[d] + (size_t)rr * a.ldc + c, z);
-        if (ARG) st_vec_cs<FV>(a.E + (size_t)rr * a.lde + c, m1);
-      }
     }
   }
 }
