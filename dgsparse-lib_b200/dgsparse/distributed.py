@@ -172,9 +172,13 @@ class EdgeShardedSDDMM:
     computed by exactly one rank with the single-GPU arithmetic, so the result is bit-identical to one GPU — unlike
     the alternative split along K, whose all-reduce changes the summation order."""
 
-    def __init__(self, rowptr, col, group=None):
-        from . import _kernels
-        self._K = _kernels
+    def __init__(self, rowptr, col, group=None, _slice_kernel=None):
+        # _slice_kernel(row, col, D1, D2, out): test hook (tests/test_distributed_cpu.py drives the sharding / exchange logic
+        # over gloo with a stand-in); the product always runs the CUDA kernel, which raises on non-CUDA tensors
+        if _slice_kernel is None:
+            from . import _kernels
+            _slice_kernel = lambda row, col, D1, D2, out: _kernels.sddmm_coo(row, col, D1, D2, out=out)
+        self._slice_kernel = _slice_kernel
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -190,7 +194,7 @@ class EdgeShardedSDDMM:
     def __call__(self, D1: torch.Tensor, D2: torch.Tensor) -> torch.Tensor:
         """D1 [M, K], D2 [ncols, K] fp32, replicated.  Returns [1, nnz] (the torch-face shape) on every rank."""
         mine = self.out[self.rank * self.chunk:(self.rank + 1) * self.chunk]
-        self._K.sddmm_coo(self.row, self.col, D1, D2, out=mine[:self.hi - self.lo])
+        self._slice_kernel(self.row, self.col, D1, D2, mine[:self.hi - self.lo])
         if self.world > 1:
             dist.all_gather_into_tensor(self.out, mine, group=self.group)   # in place: the slice is already at its offset
         return self.out[:self.nnz].reshape(1, self.nnz)

@@ -56,3 +56,41 @@ def test_shard_columns_rejects_ragged_split():
     assert shard_columns(512, 8) == [(64 * r, 64 * (r + 1)) for r in range(8)]
     with pytest.raises(ValueError):
         shard_columns(100, 8)
+
+
+def _sddmm_worker(rank, world, port, ret):
+    sys.path.insert(0, os.path.join(ROOT, "dgsparse-lib_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dgsparse.distributed import EdgeShardedSDDMM
+    g = torch.Generator().manual_seed(5)
+    M, K = 37, 8
+    deg = torch.randint(0, 6, (M,), generator=g)
+    deg[3] = 0; deg[4] = 0; deg[11] = 40                     # empty rows and a hub that straddles the shard boundary
+    rowptr = torch.zeros(M + 1, dtype=torch.int32)
+    rowptr[1:] = torch.cumsum(deg, 0).int()
+    nnz = int(rowptr[-1])
+    col = torch.randint(0, M, (nnz,), generator=g).int()
+    D1, D2 = torch.rand(M, K, generator=g), torch.rand(M, K, generator=g)
+
+    def stand_in(row, c, A, B, out):                           # what the CUDA slice kernel computes, in torch on the CPU
+        out.copy_((A[row.long()] * B[c.long()]).sum(1))
+    op = EdgeShardedSDDMM(rowptr, col, _slice_kernel=stand_in)
+    got = op(D1, D2)
+    row_full = torch.repeat_interleave(torch.arange(M), deg)
+    want = (D1[row_full] * D2[col.long()]).sum(1).reshape(1, nnz)
+    spans_ok = op.lo == min(nnz, rank * op.chunk) and op.hi == min(nnz, (rank + 1) * op.chunk)
+    ret[rank] = bool(torch.equal(got, want)) and tuple(got.shape) == (1, nnz) and spans_ok
+    dist.destroy_process_group()
+
+
+def test_edge_sharded_sddmm_exchange_logic_world2():
+    """Edge split, in-place all-gather of the slices and the [1, nnz] assembly of EdgeShardedSDDMM over gloo (the slice kernel
+    itself is CUDA-only and is checked on the GPU: tests/test_sddmm_csr2csc_gpu.py, tests/mgpu_worker.py)."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31000 + os.getpid() % 2000
+    mp.spawn(_sddmm_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
