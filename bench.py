@@ -430,7 +430,10 @@ def main():
                          "kernel_ms_avg": k_avg, "fixup_ms_avg": (sum(fix_ms) / len(fix_ms)) if fix_ms else None,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "gather_bytes_per_launch": 4.0 * nnz * N,
-                         "note": "gathered B rows (nnz*N*4 B) are served by L2, see DESIGN.md"},
+                         "l2_gather_gbs": 4.0 * nnz * N / (k_avg * 1e-3) / 1e9,
+                         "note": "gathered B rows (nnz*N*4 B) are served by L2 (l2_gather_gbs; ncu: lts__throughput 83 % of "
+                                 "peak on reddit@64, profiles/r01_ncu_full_reddit64.txt): that bandwidth, not HBM, bounds "
+                                 "the kernel when B fits L2 — see DESIGN.md 4.1"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
