@@ -103,12 +103,20 @@ __global__ void __launch_bounds__(256) fill_keys_kernel(unsigned long long *t, i
   if (i < n) t[i] = kEmptyKey;
 }
 
+// A key holds 16 bits per component: batch in [0, 65535], x / y / z in (-32768, 32768).  Anything else would alias
+// another voxel, so it raises *bad instead (kpos_kernel then poisons knnz / kpos / qkpos with -1).
+__device__ __forceinline__ bool key_in_range(const int4 v) {
+  return v.x >= 0 && v.x <= 0xffff && v.y > -kBias && v.y < kBias && v.z > -kBias && v.z < kBias && v.w > -kBias && v.w < kBias;
+}
+
 // table_keys[slot] = key, table_val[slot] = input index.  Duplicate input coordinates keep the smallest index.
 __global__ void __launch_bounds__(256) hash_insert_kernel(int n, const int *__restrict__ c, unsigned mask,
-                                                          unsigned long long *__restrict__ tkeys, int *__restrict__ tval) {
+                                                          unsigned long long *__restrict__ tkeys, int *__restrict__ tval,
+                                                          int *__restrict__ bad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int4 v = __ldg(reinterpret_cast<const int4 *>(c) + i);
+  if (!key_in_range(v)) { *bad = 1; return; }
   const unsigned long long key = pack_key(v.x, v.y, v.z, v.w);
   unsigned slot = hash_key(key) & mask;
   while (true) {
@@ -126,6 +134,7 @@ struct QueryArgs {
   const int *tval;
   int *hit;    // [k_vol][out_nnz] input index or -1
   int *flag;   // [k_vol][out_nnz] 1 / 0 (scan input)
+  int *bad;    // set when an output coordinate does not fit a key
 };
 
 // one thread per (offset k, output o), o fastest: coalesced table writes, the 27 probes of one output spread over blocks
@@ -134,6 +143,7 @@ __global__ void __launch_bounds__(256) query_kernel(const QueryArgs a) {
   if (t >= (int64_t)a.k_vol * a.out_nnz) return;
   const int k = (int)(t / a.out_nnz), o = (int)(t % a.out_nnz);
   const int4 v = __ldg(reinterpret_cast<const int4 *>(a.out_coords) + o);
+  if (!key_in_range(v)) *a.bad = 1;
   int kx = k / (a.ksz * a.ksy), ky = (k / a.ksz) % a.ksy, kz = k % a.ksz;
   int x, y, z;
   if (a.subm) {   // _queryhash_subm: centred taps
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(256) query_kernel(const QueryArgs a) {
     z = v.w * a.sz - a.pz + tap_offset(kz, a.ksz);
   }
   int found = -1;
-  if (k != a.skip_k && x > -kBias && x < kBias && y > -kBias && y < kBias && z > -kBias && z < kBias) {
+  if (k != a.skip_k && v.x >= 0 && v.x <= 0xffff && x > -kBias && x < kBias && y > -kBias && y < kBias && z > -kBias && z < kBias) {
     const unsigned long long key = pack_key(v.x, x, y, z);
     unsigned slot = hash_key(key) & a.mask;
     while (true) {
@@ -168,8 +178,13 @@ __global__ void __launch_bounds__(256) compact_kernel(int k_vol, int out_nnz, co
 
 // kpos[k] = pos[k * out_nnz]; knnz; qkpos = counts rounded up to q (exclusive_scan_for_kernel_quantified of the reference)
 __global__ void kpos_kernel(int k_vol, int out_nnz, const int *__restrict__ pos, const int *__restrict__ flag, int q, int *knnz,
-                            int *kpos, int *qkpos) {
+                            int *kpos, int *qkpos, const int *__restrict__ bad) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (*bad) {   // coordinates outside the 16-bit key range: no silent aliasing, the map is marked invalid
+    for (int k = 0; k < k_vol; k++) { knnz[k] = -1; kpos[k] = -1; qkpos[k] = -1; }
+    kpos[k_vol] = -1; qkpos[k_vol] = -1;
+    return;
+  }
   const int64_t last = (int64_t)k_vol * out_nnz - 1;
   const int total = last >= 0 ? pos[last] + flag[last] : 0;
   int qacc = 0;
@@ -300,11 +315,13 @@ cudaError_t kmap_build_ex(int in_nnz, const int *in_coords, int out_nnz, const i
   int *tval = reinterpret_cast<int *>(w); w += up256(tsize * 4ull);
   int *hit = reinterpret_cast<int *>(w); w += up256((cells > 0 ? cells : 1) * 4);
   int *flag = reinterpret_cast<int *>(w); w += up256((cells > 0 ? cells : 1) * 4);
-  int *pos = reinterpret_cast<int *>(w);
+  int *pos = reinterpret_cast<int *>(w); w += up256((cells > 0 ? cells : 1) * 4);
+  int *bad = reinterpret_cast<int *>(w);   // inside the 1 KB tail kmap_workspace_bytes() reserves
   cudaError_t e;
+  if ((e = cudaMemsetAsync(bad, 0, sizeof(int), stream)) != cudaSuccess) return e;
   fill_keys_kernel<<<(tsize + 255) / 256, 256, 0, stream>>>(tkeys, (int)tsize);
   if ((e = cudaMemsetAsync(tval, 0x7f, tsize * 4ull, stream)) != cudaSuccess) return e;
-  if (in_nnz > 0) hash_insert_kernel<<<(in_nnz + 255) / 256, 256, 0, stream>>>(in_nnz, in_coords, tsize - 1, tkeys, tval);
+  if (in_nnz > 0) hash_insert_kernel<<<(in_nnz + 255) / 256, 256, 0, stream>>>(in_nnz, in_coords, tsize - 1, tkeys, tval, bad);
   if (cells > 0) {
     QueryArgs a;
     // centre tap (k_vol / 2 for odd volumes, 0 otherwise: src/cuda/spconv_cuda.cu:35) left to spconv's separate_mid
@@ -312,13 +329,14 @@ cudaError_t kmap_build_ex(int in_nnz, const int *in_coords, int out_nnz, const i
     a.out_nnz = out_nnz; a.ksx = ksx; a.ksy = ksy; a.ksz = ksz; a.k_vol = k_vol; a.sx = sx; a.sy = sy; a.sz = sz;
     a.px = px; a.py = py; a.pz = pz; a.subm = subm;
     a.out_coords = out_coords; a.mask = tsize - 1; a.tkeys = tkeys; a.tval = tval; a.hit = hit; a.flag = flag;
+    a.bad = bad;
     const int blocks = (int)((cells + 255) / 256);
     query_kernel<<<blocks, 256, 0, stream>>>(a);
     size_t t = scan_tmp;
     if ((e = cub::DeviceScan::ExclusiveSum(tmp, t, flag, pos, (int)cells, stream)) != cudaSuccess) return e;
     compact_kernel<<<blocks, 256, 0, stream>>>(k_vol, out_nnz, hit, pos, imap, omap);
   }
-  kpos_kernel<<<1, 32, 0, stream>>>(k_vol, out_nnz, pos, flag, q, knnz, kpos, qkpos);
+  kpos_kernel<<<1, 32, 0, stream>>>(k_vol, out_nnz, pos, flag, q, knnz, kpos, qkpos, bad);
   return cudaGetLastError();
 }
 

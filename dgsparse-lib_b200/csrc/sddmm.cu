@@ -126,14 +126,14 @@ __global__ void __launch_bounds__(kSdThreads) sddmm_kernel(const SddmmArgs a) {
       for (int u = 0; u < NV; u++) {
         p[u] = 0.0f;
         const int pos = base + j0 + u;
-        const bool ok = pos < hi;           // beyond the segment: dummy edge (row 0, col 0), never stored
+        const bool ok = pos < hi;           // beyond the segment: dummy edge (current row, col 0), never stored
         cols[u] = s_col[grp][j0 + u];
         degs[u] = 1;
         if (COO) {
           rows[u] = ok ? s_row[grp][j0 + u] : 0;
         } else {
           if (ok && pos >= row_end) advance_to(pos);
-          rows[u] = ok ? r : 0;
+          rows[u] = r;                      // padding keeps the current row: rows[] stays monotone for one_row below
           if (MEAN) degs[u] = row_end - row_start;
         }
       }

@@ -12,6 +12,7 @@ from .tensor import SparseTensor
 from .storage import Storage
 from .ftransform import csr2csc
 from . import gspmm, sddmm, spconv, sparse_mapping  # noqa: F401  (spconv registers torch.ops.dgsparse_spconv.spconv)
+from . import nn  # noqa: F401,E402  (dgsparse/__init__.py:44 `from . import nn`; after SparseTensor / spmm_* exist)
 
 __version__ = "0.1+b200"
 

@@ -17,6 +17,13 @@ output panel is then made available on every rank, in one of two ways:
                panel-major [world, M, n_local] buffer (panels_to_row_major() permutes when needed).
 
 No reduction is involved, so results are bit-identical to the single-GPU kernel.
+
+Output buffering (peer / mcast): remote ranks store into this rank's C, and the only cross-rank synchronisation is the
+completion barrier AFTER the stores.  C is therefore DOUBLE-BUFFERED and alternates per call: step k+1 writes the buffer
+step k did not use, so a fast rank's step-k+1 stores cannot overwrite the step-k result a slow rank's consumer kernels are
+still reading; by the time a buffer is written again (step k+2) the writer has passed step k+1's barrier, which every rank
+enqueues on its stream behind its step-k consumers.  Contract: consume the returned tensor on the stream the op was called
+on (or order other streams behind it) and before the call after next.
 One process per GPU (torchrun); torch.distributed is used for the rendezvous, the handle exchange
 and the barrier only.
 """
@@ -63,7 +70,8 @@ class ColumnShardedSpMM:
         self.reduce, self.compute = reduce, compute
         dev = col.device
         self.ws = torch.empty(max(256, _lib.lib.dgs_spmm_workspace_bytes(n_local, self.nnz, 0)), dtype=torch.uint8, device=dev)
-        self.C = None
+        self.C = None          # [2, M, n_total]: double-buffered output (see the module docstring), index = call parity
+        self._calls = 0
         self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._opened = []
         self.mode = mode or ("mcast" if self.world > 1 else "local")
@@ -77,7 +85,8 @@ class ColumnShardedSpMM:
             if any(m != "mcast" for m in agreed):
                 self.mode = "peer"
         if self.C is None or self.mode != "mcast":
-            self.C = torch.empty((self.M, self.n_total), dtype=torch.float32, device=dev)
+            nbuf = 2 if self.world > 1 and self.mode == "peer" else 1
+            self.C = torch.empty((nbuf, self.M, self.n_total), dtype=torch.float32, device=dev)
         if self.world > 1 and self.mode == "peer":
             try:
                 self._map_peers()
@@ -95,7 +104,7 @@ class ColumnShardedSpMM:
         """C in torch symmetric memory (plumbing: allocation + rendezvous); the kernel only needs the multicast address."""
         import torch.distributed._symmetric_memory as symm
         group = self.group if self.group is not None else dist.group.WORLD
-        C = symm.empty((self.M, self.n_total), dtype=torch.float32, device=dev)
+        C = symm.empty((2, self.M, self.n_total), dtype=torch.float32, device=dev)
         hdl = symm.rendezvous(C, group)
         mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
         if mc == 0:
@@ -121,7 +130,8 @@ class ColumnShardedSpMM:
             ptrs.append(base + self.lo * 4)          # every destination gets THIS rank's column panel
         # dst[0] must be the local C
         ptrs = [ptrs[self.rank]] + [p for r, p in enumerate(ptrs) if r != self.rank]
-        self._dst = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        buf_bytes = self.M * self.n_total * 4
+        self._dst = [(ctypes.c_void_p * len(ptrs))(*[p + b * buf_bytes for p in ptrs]) for b in range(2)]
 
     def __call__(self, B_local: torch.Tensor) -> torch.Tensor:
         """B_local: [K, n_local] fp32 (this rank's column panel).  Returns row-major C[M, n_total] (peer /
@@ -135,22 +145,25 @@ class ColumnShardedSpMM:
                                      self.reduce, self.compute, ptr(self.ws), self.ws.numel(), stream), "dgs_spmm_csr")
             dist.all_gather_into_tensor(self.panels, self.C_local, group=self.group)
             return self.panels
+        buf = self._calls & 1 if self.C.shape[0] == 2 else 0
+        self._calls += 1
         if self.mode == "mcast":
             L.check(lib.dgs_spmm_csr_mcast(self.M, self.n_local, self.nnz, ptr(self.rowptr), ptr(self.col), ptr(self.values),
-                                           ptr(B_local), B_local.stride(0), self._mc_dst, self.n_total, self.reduce,
+                                           ptr(B_local), B_local.stride(0), self._mc_dst + buf * self.M * self.n_total * 4,
+                                           self.n_total, self.reduce,
                                            self.compute, ptr(self.ws), self.ws.numel(), stream), "dgs_spmm_csr_mcast")
             dist.all_reduce(self._flag, group=self.group)   # completion barrier: every rank's multicast stores have landed
-            return self.C
+            return self.C[buf]
         if self.mode == "local":
             dst = (ctypes.c_void_p * 1)(self.C.data_ptr())
         else:
-            dst = self._dst
+            dst = self._dst[buf]
         L.check(lib.dgs_spmm_csr_multi(self.M, self.n_local, self.nnz, ptr(self.rowptr), ptr(self.col), ptr(self.values),
                                        ptr(B_local), B_local.stride(0), len(dst), dst, self.n_total, self.reduce,
                                        self.compute, ptr(self.ws), self.ws.numel(), stream), "dgs_spmm_csr_multi")
         if self.world > 1:
             dist.all_reduce(self._flag, group=self.group)   # completion barrier: all peers' stores have landed
-        return self.C
+        return self.C[buf]
 
     def close(self):
         for p in self._opened:

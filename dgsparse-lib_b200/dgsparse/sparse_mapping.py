@@ -33,6 +33,19 @@ class KernelMap:
     separate_mid: bool
 
 
+def _check_coords(c: torch.Tensor):
+    """The kernels pack a voxel into one 64-bit key, 16 bits per component: reject what would alias another voxel."""
+    if c.dtype != torch.int32 or c.dim() != 2 or c.size(1) != 4:
+        raise TypeError("in_coords must be int32 [n, 4] = (batch, x, y, z)")
+    if c.size(0) == 0:
+        return
+    xyz, b = c[:, 1:], c[:, 0]
+    lo, hi, bmin, bmax = (int(v) for v in torch.stack([xyz.amin(), xyz.amax(), b.amin(), b.amax()]).tolist())
+    if lo <= -32768 or hi >= 32768 or bmin < 0 or bmax > 65535:
+        raise ValueError(f"voxel coordinates must lie in (-32768, 32768) and batch indices in [0, 65535] "
+                         f"(got coordinate range [{lo}, {hi}], batch range [{bmin}, {bmax}])")
+
+
 def _triple(v):
     return (v, v, v) if isinstance(v, int) else tuple(int(x) for x in v)
 
@@ -41,8 +54,7 @@ def downsample_coords(in_coords: torch.Tensor, stride) -> torch.Tensor:
     """Sorted unique of (batch, floor(x/sx), floor(y/sy), floor(z/sz)) — coordsDownsample + sort + unique,
     src/cuda/sparse_mapping.cu:68-97 (coordinates in OUTPUT resolution)."""
     require_cuda(in_coords)
-    if in_coords.dtype != torch.int32 or in_coords.dim() != 2 or in_coords.size(1) != 4:
-        raise TypeError("in_coords must be int32 [n, 4] = (batch, x, y, z)")
+    _check_coords(in_coords)
     c = in_coords.contiguous()
     n = c.size(0)
     sx, sy, sz = _triple(stride)
@@ -60,8 +72,7 @@ def expand_coords(in_coords: torch.Tensor, kernel_size, stride, padding=0, min_c
     sorted unique of (in - off(tap) + padding) / stride over every (input, tap) whose division is exact and whose result
     lies in [min_coord, max_coord] (output resolution; None = unbounded)."""
     require_cuda(in_coords)
-    if in_coords.dtype != torch.int32 or in_coords.dim() != 2 or in_coords.size(1) != 4:
-        raise TypeError("in_coords must be int32 [n, 4] = (batch, x, y, z)")
+    _check_coords(in_coords)
     c = in_coords.contiguous()
     n = c.size(0)
     ks, st, pd = _triple(kernel_size), _triple(stride), _triple(padding)
@@ -90,8 +101,7 @@ def build_kernel_map(in_coords: torch.Tensor, kernel_size=3, stride=1, separate_
     ks, st = _triple(kernel_size), _triple(stride)
     pd = _triple(padding) if padding is not None else (0, 0, 0)
     c = in_coords.contiguous()
-    if c.dtype != torch.int32 or c.dim() != 2 or c.size(1) != 4:
-        raise TypeError("in_coords must be int32 [n, 4] = (batch, x, y, z)")
+    _check_coords(c)
     sub = st == (1, 1, 1) and padding is None
     if separate_mid and not sub:
         raise ValueError("separate_mid needs a submanifold layer (stride 1, padding None)")
@@ -117,4 +127,6 @@ def build_kernel_map(in_coords: torch.Tensor, kernel_size=3, stride=1, separate_
                                     ptr(kpos), ptr(qkpos), ptr(ws), ws.numel(), stream_of(c)), "dgs_kmap_build_ex")
         ends = torch.stack([kpos[-1], qkpos[-1]]).cpu()
     pairs, sum_nnz = int(ends[0]), int(ends[1])
+    if pairs < 0:   # the kernels found a coordinate outside the 16-bit key range (dgs_kmap_build_ex poisons kpos with -1)
+        raise ValueError("kernel map: a coordinate does not fit the 16-bit-per-component voxel key")
     return KernelMap(out_coords, imap[:pairs], omap[:pairs], knnz, kpos, qkpos, n_out, sum_nnz, separate_mid)

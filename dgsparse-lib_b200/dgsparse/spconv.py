@@ -42,7 +42,9 @@ def quantize_kpos(knnz, q=128):
 
 
 def _workspace(nbytes, device):
-    key = (device.type, device.index)
+    # one scratch per (device, stream): the kernels of a call read the prepared weights from it, so two streams running
+    # spconv concurrently must not share it (reuse on ONE stream is ordered by the stream)
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _ws.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)

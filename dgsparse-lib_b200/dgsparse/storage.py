@@ -46,7 +46,10 @@ class Storage(object):
             assert rowptr.numel() - 1 == self.sparse_sizes[0]
             rowptr = rowptr.contiguous()
         else:
-            # COO rows (sorted) -> rowptr; the reference leaves rowptr None and then fails in csr2csc
+            # COO rows -> rowptr; the reference leaves rowptr None and then fails in csr2csc.  (row, col, values) must
+            # already be in CSR order (row non-decreasing): bincount + cumsum is only a row pointer for sorted rows.
+            if row.numel() > 1 and not bool((row[1:] >= row[:-1]).all()):
+                raise ValueError("Storage: COO `row` must be sorted (non-decreasing); sort (row, col, values) together first")
             counts = torch.bincount(row.long(), minlength=M)
             rowptr = torch.zeros(M + 1, dtype=torch.int32, device=col.device)
             rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
@@ -112,7 +115,12 @@ class Storage(object):
 
     def csr2csc_convert(self):
         """Eager CSC build, as dgsparse/storage.py:100,159-174: sets _colptr, _row (CSC row indices)
-        and _csr2csc (CSC position -> CSR position)."""
+        and _csr2csc (CSC position -> CSR position).
+
+        Deviation: `_row` is ALWAYS replaced by the CSC-ordered row indices, because that is what the backward kernels read
+        it as (src/spmm.cpp:52-80 passes it as the CSC index array).  The reference keeps a user-supplied COO `row`
+        (`if self._row is None`), i.e. CSR-ordered rows, and its backward then gathers with the wrong indices; after this
+        call `row()` therefore returns CSC order here, whatever was passed to the constructor."""
         if self._csr2csc is not None:
             return self._csr2csc
         if not self._col.is_cuda:

@@ -241,15 +241,31 @@ void oracle_csr2csc(int M, int ncols, const int *rowptr, const int *col, const f
 
 /* Sparse 3-D convolution gather-GEMM-scatter, test/test_spconv.py:17-53 (cpu_compute):
  * for each kernel offset k and each pair p in [kpos[k], kpos[k+1]):
- *   out[omap[p], :] += in[imap[p], :] @ W[k]        W: [k_vol, c_in, c_out] row-major. */
+ *   out[omap[p], :] += in[imap[p], :] @ W[k]        W: [k_vol, c_in, c_out] row-major;
+ * then, with `precompute` (test_spconv.py:46-52, the separate_mid form of a submanifold layer):
+ *   out[i, :] += in[i, :] @ W[mid_k] for every output row i, mid_k = k_vol / 2 for odd k_vol, else 0.
+ * Per output element the additions happen in the same order as cpu_compute (k, pair, c_in ascending; product
+ * rounded to fp32, then added), so the result is bit-identical to it (pinned by tests/test_oracle_golden.py). */
 void oracle_spconv(int k_vol, int c_in, int c_out, int out_nnz, const int *kpos, const int *imap,
-                   const int *omap, const float *in, const float *W, float *out) {
+                   const int *omap, const float *in, const float *W, float *out, int precompute) {
   memset(out, 0, sizeof(float) * (size_t)out_nnz * c_out);
   for (int k = 0; k < k_vol; k++) {
     const float *Wk = W + (size_t)k * c_in * c_out;
     for (int p = kpos[k]; p < kpos[k + 1]; p++) {
       const float *x = in + (size_t)imap[p] * c_in;
       float *y = out + (size_t)omap[p] * c_out;
+      for (int ci = 0; ci < c_in; ci++) {
+        float xv = x[ci];
+        for (int co = 0; co < c_out; co++) y[co] += xv * Wk[(size_t)ci * c_out + co];
+      }
+    }
+  }
+  if (precompute) {
+    const int mid_k = (k_vol % 2 == 1) ? k_vol / 2 : 0;
+    const float *Wk = W + (size_t)mid_k * c_in * c_out;
+    for (int i = 0; i < out_nnz; i++) {
+      const float *x = in + (size_t)i * c_in;
+      float *y = out + (size_t)i * c_out;
       for (int ci = 0; ci < c_in; ci++) {
         float xv = x[ci];
         for (int co = 0; co < c_out; co++) y[co] += xv * Wk[(size_t)ci * c_out + co];

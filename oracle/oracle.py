@@ -151,6 +151,26 @@ def ref_gspmm_module():
         return _ref_gspmm
 
 
+_ref_spconv = None
+
+
+def ref_spconv_module():
+    """The reference's own sparse-convolution CUDA behind a no-algorithm pybind shim (oracle/_ref/_ref_spconv.so, built by
+    oracle/build_ref_spconv.sh from src/cuda/sparse_mapping.cu + src/cuda/spconv_cuda.cu unmodified) or None:
+    sparse_mapping(...), spconv_fwd_fused(...), spconv_bwd_fused(...) on CUDA tensors."""
+    global _ref_spconv
+    with _lock:
+        path = os.path.join(_HERE, "_ref", "_ref_spconv.so")
+        if _ref_spconv is None and os.path.exists(path):
+            import importlib.util
+            import torch  # noqa: F401  (libtorch must be loaded before the extension)
+            spec = importlib.util.spec_from_file_location("_ref_spconv", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            _ref_spconv = mod
+        return _ref_spconv
+
+
 def num_threads():
     return int(lib().oracle_num_threads())
 
@@ -239,13 +259,14 @@ def csr2csc(rowptr, col, val=None, ncols=None):
     return colptr, row, val_t, perm
 
 
-def spconv(kpos, imap, omap, in_feats, W, out_nnz):
+def spconv(kpos, imap, omap, in_feats, W, out_nnz, precompute=False):
+    """cpu_compute(feats, weights, out_size, knnz, imap, omap, precompute), test/test_spconv.py:17-53."""
     kpos, imap, omap, in_feats, W = _i32(kpos), _i32(imap), _i32(omap), _f32(in_feats), _f32(W)
     k_vol, c_in, c_out = W.shape
     out = np.empty((out_nnz, c_out), np.float32)
     lib().oracle_spconv(ctypes.c_int(k_vol), ctypes.c_int(c_in), ctypes.c_int(c_out),
                         ctypes.c_int(out_nnz), _p(kpos, _i32p), _p(imap, _i32p), _p(omap, _i32p),
-                        _p(in_feats, _f32p), _p(W, _f32p), _p(out, _f32p))
+                        _p(in_feats, _f32p), _p(W, _f32p), _p(out, _f32p), ctypes.c_int(int(bool(precompute))))
     return out
 
 

@@ -14,6 +14,12 @@
 3. <name>_sddmm32.npz    golden SDDMM output (sddmm_reference_host, sp_util.hpp:87-112), K=32.
 4. spconv_*.npz          the kernel maps of example/data/sample-data/fp32/minkunet-semantickitti/*.pth
                          (kpos, imap, omap, sizes) re-saved without pickle, for the spconv tier.
+5. spconv_cpu_compute.npz  golden OUTPUTS of the reference's own `cpu_compute` (test/test_spconv.py:17-53, imported
+                         from /root/reference/test/test_spconv.py and run unmodified) on a sub-layer cut out of the
+                         c_in = 4 MinkUNet fixture: the pairs among ~500 voxels (a closed sub-layer, in_nnz == out_nnz), renumbered so that
+                         the Python quadruple loop finishes in about a minute.  Both call forms: all taps in the maps
+                         (precompute = False) and the centre tap taken out and added by `precompute = True`.
+                         tests/test_oracle_golden.py pins oracle_spconv to these bit for bit.
 """
 import os
 import sys
@@ -76,6 +82,52 @@ def main():
             print("spconv", f, {k: (v.shape, v.dtype) for k, v in keep.items()})
     except Exception as e:  # pragma: no cover
         print("spconv fixtures skipped:", e)
+    spconv_cpu_compute_golden()
+
+
+def spconv_cpu_compute_golden(n_out=500):
+    """Run the reference's own cpu_compute on a sub-layer of the c_in = 4 fixture and store inputs + outputs."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("ref_test_spconv", "/root/reference/test/test_spconv.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)                      # defines kpos_quantized / cpu_compute / remove_mid / test_spconv only
+    g = np.load(os.path.join(OUT, "spconv_fp32_0.npz"))
+    k_vol, c_in, c_out = int(g["k_vol"]), int(g["c_in"]), int(g["c_out"])
+    kpos, imap, omap = g["kpos"], g["imap"], g["omap"]
+    assert c_in == 4 and int(g["in_nnz"]) == int(g["out_nnz"])
+    rng = np.random.default_rng(2024)
+    # ~n_out output voxels: a contiguous run (neighbours of neighbours are likely inside) plus scattered ones
+    start = int(rng.integers(0, int(g["out_nnz"]) - n_out))
+    keep_out = np.unique(np.concatenate([np.arange(start, start + n_out - 40), rng.choice(int(g["out_nnz"]), 40, replace=False)]))
+    # a CLOSED sub-layer: pairs whose input and output voxel are both kept, so in_nnz == out_nnz == |kept| and the
+    # separate_mid form (which the op only accepts for in_nnz == out_nnz, src/cuda/spconv_cuda.cu:61-82) can be driven too
+    sel = np.isin(omap, keep_out) & np.isin(imap, keep_out)
+    tap = np.repeat(np.arange(k_vol), np.diff(kpos))
+    order = keep_out
+    newid = -np.ones(int(g["in_nnz"]), np.int64)
+    newid[order] = np.arange(order.size)
+    imap_s, omap_s, tap_s = newid[imap[sel]].astype(np.int32), newid[omap[sel]].astype(np.int32), tap[sel]
+    knnz_s = np.bincount(tap_s, minlength=k_vol).astype(np.int32)
+    kpos_s = np.concatenate([[0], np.cumsum(knnz_s)]).astype(np.int32)
+    feats = rng.uniform(-1, 1, (order.size, c_in)).astype(np.float32)
+    W = rng.uniform(-1, 1, (k_vol, c_in, c_out)).astype(np.float32)
+    out_size = keep_out.size
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    full = ref.cpu_compute(t(feats), t(W), out_size, t(knnz_s), t(imap_s), t(omap_s), False).numpy()
+    # the separate_mid form: centre tap removed from the maps, added by precompute=True
+    mid = k_vol // 2
+    s, e = int(kpos_s[mid]), int(kpos_s[mid + 1])
+    assert np.array_equal(imap_s[s:e], omap_s[s:e]) and e - s == out_size     # the centre tap is the identity map
+    imap_m, omap_m = np.delete(imap_s, np.s_[s:e]), np.delete(omap_s, np.s_[s:e])
+    knnz_m = knnz_s.copy()
+    knnz_m[mid] = 0
+    sep = ref.cpu_compute(t(feats), t(W), out_size, t(knnz_m), t(imap_m), t(omap_m), True).numpy()
+    np.savez_compressed(os.path.join(OUT, "spconv_cpu_compute.npz"), feats=feats, W=W, out_size=np.array(out_size),
+                        knnz=knnz_s, imap=imap_s, omap=omap_s, out_full=full,
+                        knnz_mid=knnz_m, imap_mid=imap_m, omap_mid=omap_m, out_separate_mid=sep)
+    print("spconv cpu_compute golden:", out_size, "outputs,", order.size, "inputs,", int(knnz_s.sum()), "pairs,",
+          "max |full - separate_mid| =", float(np.abs(full - sep).max()))
 
 
 if __name__ == "__main__":

@@ -144,3 +144,15 @@ def test_spconv_oracle_on_fixture(oracle):
         s, e = kpos[k], kpos[k + 1]
         np.add.at(ref, omap[s:e], x[imap[s:e]].astype(np.float64) @ W[k].astype(np.float64))
     assert np.allclose(out, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_spconv_oracle_pinned_to_reference_cpu_compute(oracle):
+    """oracle_spconv against golden OUTPUTS of the reference's own cpu_compute (test/test_spconv.py:17-53), generated by
+    tests/golden/make_fixtures.py (which imports and runs that function unmodified): bit for bit, both call forms."""
+    g = np.load(os.path.join(GOLDEN, "spconv_cpu_compute.npz"))
+    out_size = int(g["out_size"])
+    for knnz, imap, omap, pre, want in ((g["knnz"], g["imap"], g["omap"], False, g["out_full"]),
+                                        (g["knnz_mid"], g["imap_mid"], g["omap_mid"], True, g["out_separate_mid"])):
+        kpos = np.concatenate([[0], np.cumsum(knnz)]).astype(np.int32)
+        got = oracle.spconv(kpos, imap, omap, g["feats"], g["W"], out_size, precompute=pre)
+        assert got.dtype == np.float32 and np.array_equal(got, want), float(np.abs(got - want).max())

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import assert_close_f32
+from util import assert_close_f32, sddmm_absref, spmm_absref
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -59,11 +59,43 @@ def test_sddmm_widths(K, oracle, graphs, Kd):
     for mean in (False, True):
         out = K.sddmm_csr(dev(rowptr), dev(col), dev(D1), dev(D2), mean=mean).cpu().numpy()[0]
         assert_close_f32(out, oracle.sddmm_csr(rowptr, col, D1, D2, mean), oracle.sddmm_csr(rowptr, col, D1, D2, mean, f64=True),
-                         what=f"K={Kd} mean={mean}")
+                         what=f"K={Kd} mean={mean}", absref=sddmm_absref(oracle, rowptr, col, D1, D2, mean))
     row = np.repeat(np.arange(M, dtype=np.int32), np.diff(rowptr))
     perm = np.random.default_rng(1).permutation(col.size)       # COO needs no ordering
     out = K.sddmm_coo(dev(row[perm]), dev(col[perm]), dev(D1), dev(D2)).cpu().numpy()
-    assert_close_f32(out, oracle.sddmm_coo(row[perm], col[perm], D1, D2), what=f"coo K={Kd}")
+    assert_close_f32(out, oracle.sddmm_coo(row[perm], col[perm], D1, D2), what=f"coo K={Kd}",
+                     absref=sddmm_absref(oracle, rowptr, col, D1, D2)[perm])
+
+
+@pytest.mark.parametrize("Kd", [8, 30, 64, 256])
+@pytest.mark.parametrize("nnz_shape", ["1", "3", "7", "9", "hub0_tail", "hub0_33"])
+def test_sddmm_tiny_and_hub_row0(K, oracle, graphs, Kd, nnz_shape):
+    """the last (ragged) edge group of a matrix whose row 0 reaches it — rows [0,1,2,pad..] — must not be
+    multiplied with D1[row 0] throughout.  nnz in {1,3,7,9} and a hub row 0 followed by short rows, every kernel family
+    (register-staged K<64 / unaligned K, ring K>=64), plain / MEAN / masked."""
+    M, Kc = 12, 17
+    if nnz_shape.isdigit():
+        rows = (np.arange(int(nnz_shape)) % M).astype(np.int32)     # rows 0, 1, 2, ...: row 0 first, other rows after it
+    elif nnz_shape == "hub0_tail":
+        rows = np.array([0] * 29 + [1, 2, 5], np.int32)               # last 8-group starts in row 0 and ends in row 5
+    else:
+        rows = np.array([0] * 33 + [3, 4], np.int32)
+    col = (np.arange(rows.size, dtype=np.int32) * 5 + 3) % Kc
+    rowptr = np.zeros(M + 1, np.int32)
+    np.add.at(rowptr, rows + 1, 1)
+    rowptr = np.cumsum(rowptr).astype(np.int32)
+    order = np.lexsort((col, rows))
+    col = col[order].astype(np.int32)
+    D1 = graphs.uniform(M * Kd, 31, -1, 1).reshape(M, Kd)
+    D2 = graphs.uniform(Kc * Kd, 32, -1, 1).reshape(Kc, Kd)
+    for mean in (False, True):
+        out = K.sddmm_csr(dev(rowptr), dev(col), dev(D1), dev(D2), mean=mean).cpu().numpy()[0]
+        assert_close_f32(out, oracle.sddmm_csr(rowptr, col, D1, D2, mean), oracle.sddmm_csr(rowptr, col, D1, D2, mean, f64=True),
+                         what=f"tiny {nnz_shape} K={Kd} mean={mean}", absref=sddmm_absref(oracle, rowptr, col, D1, D2, mean))
+    E = ((np.arange(M * Kd, dtype=np.int64) * 7) % Kc).astype(np.int32).reshape(M, Kd)
+    got = K.sddmm_csr(dev(rowptr), dev(col), dev(D1), dev(D2), E=dev(E)).cpu().numpy()[0]
+    assert_close_f32(got, oracle.sddmm_csr_mask(rowptr, col, D1, D2, E), what=f"tiny masked {nnz_shape} K={Kd}",
+                     absref=sddmm_absref(oracle, rowptr, col, D1, D2))
 
 
 def test_sddmm_arxiv_like_k256(K, oracle, graphs):
@@ -73,7 +105,8 @@ def test_sddmm_arxiv_like_k256(K, oracle, graphs):
     D1 = graphs.uniform(M * 256, 1).reshape(M, 256)
     D2 = graphs.uniform(M * 256, 2).reshape(M, 256)
     out = K.sddmm_csr(dev(rowptr), dev(col), dev(D1), dev(D2)).cpu().numpy()[0]
-    assert_close_f32(out, oracle.sddmm_csr(rowptr, col, D1, D2), oracle.sddmm_csr(rowptr, col, D1, D2, f64=True), what="arxiv")
+    ref64 = oracle.sddmm_csr(rowptr, col, D1, D2, f64=True)
+    assert_close_f32(out, oracle.sddmm_csr(rowptr, col, D1, D2), ref64, what="arxiv", absref=ref64)   # inputs >= 0
 
 
 def test_masked_kernels(K, oracle, graphs):
@@ -86,9 +119,11 @@ def test_masked_kernels(K, oracle, graphs):
     _, E = oracle.spmm(rowptr, col, val, B, "max", with_arg=True)
     colptr, row, val_t, perm = oracle.csr2csc(rowptr, col, val, ncols=Kc)
     got = K.spmm_with_mask(dev(colptr), dev(row), dev(val_t), dev(G), dev(E)).cpu().numpy()
-    assert_close_f32(got, oracle.spmm_mask(colptr, row, val_t, G, E), what="spmm_mask")
+    assert_close_f32(got, oracle.spmm_mask(colptr, row, val_t, G, E), what="spmm_mask",
+                     absref=spmm_absref(oracle, colptr, row, val_t, G))       # the unmasked sum of |terms| bounds the masked one
     got = K.sddmm_csr(dev(rowptr), dev(col), dev(G), dev(B), E=dev(E)).cpu().numpy()[0]
-    assert_close_f32(got, oracle.sddmm_csr_mask(rowptr, col, G, B, E), what="sddmm_mask")
+    assert_close_f32(got, oracle.sddmm_csr_mask(rowptr, col, G, B, E), what="sddmm_mask",
+                     absref=sddmm_absref(oracle, rowptr, col, G, B))
 
 
 @pytest.mark.parametrize("name", ["p2p-Gnutella31", "ca-CondMat"])

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import assert_close_f32
+from util import assert_close_f32, sddmm_absref, spmm_absref
 
 pytestmark = pytest.mark.gpu
 
@@ -37,7 +37,7 @@ def L():
 
 @pytest.mark.parametrize("name", ["p2p-Gnutella31", "ca-CondMat"])
 @pytest.mark.parametrize("N", [32, 64, 128])
-def test_spmm_cuda_same_as_reference(R, L, graphs, name, N):
+def test_spmm_cuda_same_as_reference(R, L, oracle, graphs, name, N):
     rowptr, col, (M, Kc) = graphs.load_fixture(name)
     val = graphs.uniform(col.size, 5, 0.5, 1.5)
     B = graphs.uniform(Kc * N, 6, -1.0, 1.0).reshape(Kc, N)
@@ -48,14 +48,16 @@ def test_spmm_cuda_same_as_reference(R, L, graphs, name, N):
     L.lib.spmm_cuda(M, N, *[t.data_ptr() for t in d], ours.data_ptr())
     R.spmm_cuda(M, N, *[t.data_ptr() for t in d], ref.data_ptr())
     torch.cuda.synchronize()
-    assert_close_f32(ours.cpu().numpy(), ref.cpu().numpy(), what=f"{name} N={N} vs reference CUDA")
+    assert_close_f32(ours.cpu().numpy(), ref.cpu().numpy(), what=f"{name} N={N} vs reference CUDA",
+                     absref=spmm_absref(oracle, rowptr, col, val, B))
     # no-edge-value entry point
     ours2 = torch.empty(M, N, device="cuda")
     ref2 = torch.zeros(M, N, device="cuda")
     L.lib.spmm_cuda_no_edge_value(M, N, d[0].data_ptr(), d[1].data_ptr(), None, d[3].data_ptr(), ours2.data_ptr())
     R.spmm_cuda_no_edge_value(M, N, d[0].data_ptr(), d[1].data_ptr(), None, d[3].data_ptr(), ref2.data_ptr())
     torch.cuda.synchronize()
-    assert_close_f32(ours2.cpu().numpy(), ref2.cpu().numpy(), what=f"{name} N={N} no-value vs reference CUDA")
+    assert_close_f32(ours2.cpu().numpy(), ref2.cpu().numpy(), what=f"{name} N={N} no-value vs reference CUDA",
+                     absref=spmm_absref(oracle, rowptr, col, None, B))
 
 
 @pytest.mark.parametrize("alg", [0, 1, 8])   # SEQREDUCE_ROWBALANCE, PARREDUCE_ROWBALANCE, ROWCACHING_ROWBALANCE
@@ -72,11 +74,12 @@ def test_gespmm_algorithms_agree_with_ours(R, L, oracle, graphs, alg):
     ours = torch.empty(M, N, device="cuda")
     L.lib.spmm_cuda(M, N, *[t.data_ptr() for t in d], ours.data_ptr())
     torch.cuda.synchronize()
-    assert_close_f32(ours.cpu().numpy(), ref.cpu().numpy(), what=f"gespmm alg {alg}")
+    assert_close_f32(ours.cpu().numpy(), ref.cpu().numpy(), what=f"gespmm alg {alg}",
+                     absref=spmm_absref(oracle, rowptr, col, val, B))
 
 
 @pytest.mark.parametrize("K", [32, 64, 256])
-def test_sddmm_cuda_same_as_reference(R, L, graphs, K):
+def test_sddmm_cuda_same_as_reference(R, L, oracle, graphs, K):
     rowptr, col, (M, Kc) = graphs.load_fixture("p2p-Gnutella31")
     nnz = int(col.size)
     D1 = graphs.uniform(M * K, 7, -1.0, 1.0).reshape(M, K)
@@ -89,7 +92,7 @@ def test_sddmm_cuda_same_as_reference(R, L, graphs, K):
     R.sddmm_cuda_csr(M, K, nnz, *[t.data_ptr() for t in d], ref.data_ptr())
     torch.cuda.synchronize()
     assert_close_f32(ours.cpu().numpy(), ref.cpu().numpy(), what=f"sddmm K={K} vs reference CUDA",
-                     scale=float(K) ** 0.5)
+                     absref=sddmm_absref(oracle, rowptr, col, D1, D2))
     # COO entry point
     row = np.repeat(np.arange(M, dtype=np.int32), np.diff(rowptr))
     ours2 = torch.empty(nnz, device="cuda")
@@ -99,7 +102,7 @@ def test_sddmm_cuda_same_as_reference(R, L, graphs, K):
     R.sddmm_cuda_coo(K, nnz, dr.data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), ref2.data_ptr())
     torch.cuda.synchronize()
     assert_close_f32(ours2.cpu().numpy(), ref2.cpu().numpy(), what=f"sddmm coo K={K} vs reference CUDA",
-                     scale=float(K) ** 0.5)
+                     absref=sddmm_absref(oracle, rowptr, col, D1, D2))
 
 
 @pytest.mark.parametrize("nv", [1, 2, 8, 32])
@@ -120,9 +123,9 @@ def test_older_api_cuda_csr_coo_spmm(R, L, oracle, graphs, alg, nv):
     L.lib.cuda_csr_coo_spmm(*args, ours.data_ptr())
     R.cuda_csr_coo_spmm(*args, ref.data_ptr())
     torch.cuda.synchronize()
-    want = oracle.spmm(rowptr, col, val, B)
-    assert_close_f32(ours.cpu().numpy(), want, oracle.spmm_f64(rowptr, col, val, B), what=f"older api alg={alg} nv={nv}")
-    assert_close_f32(ref.cpu().numpy(), want, oracle.spmm_f64(rowptr, col, val, B), what=f"reference alg={alg} nv={nv}")
+    want, want64, T = oracle.spmm(rowptr, col, val, B), oracle.spmm_f64(rowptr, col, val, B), spmm_absref(oracle, rowptr, col, val, B)
+    assert_close_f32(ours.cpu().numpy(), want, want64, what=f"older api alg={alg} nv={nv}", absref=T)
+    assert_close_f32(ref.cpu().numpy(), want, want64, what=f"reference alg={alg} nv={nv}", absref=T)
     if alg >= 2:   # COO entry without a row pointer: rebuilt from rowIdx
         ours2 = torch.full((M, nv), float("nan"), device="cuda")
         L.lib.cuda_csr_coo_spmm(alg, 0, M, Kc, int(col.size), nv, None, d_row.data_ptr(), d_col.data_ptr(), d_val.data_ptr(),
@@ -149,6 +152,6 @@ def test_older_api_cuda_csr_spmm(R, L, oracle, graphs, layout):
     o, r = ours.cpu().numpy().reshape(shape), ref.cpu().numpy().reshape(shape)
     if layout == 0:
         o, r = o.T, r.T
-    want = oracle.spmm(rowptr, col, val, B)
-    assert_close_f32(o, want, oracle.spmm_f64(rowptr, col, val, B), what=f"cuda_csr_spmm layout={layout}")
-    assert_close_f32(r, want, oracle.spmm_f64(rowptr, col, val, B), what=f"reference cuda_csr_spmm layout={layout}")
+    want, want64, T = oracle.spmm(rowptr, col, val, B), oracle.spmm_f64(rowptr, col, val, B), spmm_absref(oracle, rowptr, col, val, B)
+    assert_close_f32(o, want, want64, what=f"cuda_csr_spmm layout={layout}", absref=T)
+    assert_close_f32(r, want, want64, what=f"reference cuda_csr_spmm layout={layout}", absref=T)

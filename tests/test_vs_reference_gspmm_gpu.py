@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import assert_close_f32
+from util import assert_close_f32, spmm_absref
 
 pytestmark = pytest.mark.gpu
 
@@ -29,7 +29,7 @@ def REF(oracle):
 @pytest.mark.parametrize("N", [32, 64, 128])
 @pytest.mark.parametrize("compute", ["add", "sub", "mul", "div"])
 @pytest.mark.parametrize("reduce", ["sum", "max", "min", "mean"])
-def test_u_op_e_reduce_same_as_reference(REF, graphs, compute, reduce, N):
+def test_u_op_e_reduce_same_as_reference(REF, oracle, graphs, compute, reduce, N):
     import dgsparse.gspmm as G
     rowptr, col, (M, Kc) = graphs.load_fixture("p2p-Gnutella31")     # 46 199 empty rows, max degree 78
     val = graphs.uniform(col.size, 3, 0.5, 1.5)
@@ -41,11 +41,12 @@ def test_u_op_e_reduce_same_as_reference(REF, graphs, compute, reduce, N):
     if reduce in ("max", "min"):
         assert torch.equal(ours, theirs)
     else:
-        assert_close_f32(ours.cpu().numpy(), theirs.cpu().numpy(), what=f"u_{compute}_e_{reduce} N={N}")
+        assert_close_f32(ours.cpu().numpy(), theirs.cpu().numpy(), what=f"u_{compute}_e_{reduce} N={N}",
+                         absref=spmm_absref(oracle, rowptr, col, val, B, reduce, compute))
 
 
 @pytest.mark.parametrize("reduce", ["sum", "max", "min", "mean"])
-def test_copy_u_same_as_reference(REF, graphs, reduce):
+def test_copy_u_same_as_reference(REF, oracle, graphs, reduce):
     import dgsparse.gspmm as G
     M, Kc, N = 6000, 5000, 64
     rowptr, col = graphs.random_csr(M, Kc, 200000, 17, empty_frac=0.3, hub=2)
@@ -57,4 +58,5 @@ def test_copy_u_same_as_reference(REF, graphs, reduce):
     if reduce in ("max", "min"):
         assert torch.equal(ours, theirs)
     else:
-        assert_close_f32(ours.cpu().numpy(), theirs.cpu().numpy(), what=f"copy_u_{reduce}")
+        assert_close_f32(ours.cpu().numpy(), theirs.cpu().numpy(), what=f"copy_u_{reduce}",
+                         absref=spmm_absref(oracle, rowptr, col, None, B, reduce))

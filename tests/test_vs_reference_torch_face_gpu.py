@@ -17,7 +17,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import assert_close_f32
+from util import assert_close_f32, sddmm_absref, spmm_absref
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -56,20 +56,25 @@ def ours(case, op):
 
 
 @pytest.mark.parametrize("op", ["sum", "max", "min", "mean"])
-def test_forward_same_as_reference_torch_op(case, op):
+def test_forward_same_as_reference_torch_op(case, oracle, op):
     y, _, _, _ = ours(case, op)
     want = case["ref"][op + "_out"]
     if op in ("max", "min"):
         assert np.array_equal(y, want)
     else:
-        assert_close_f32(y, want, what=f"spmm_{op} forward vs reference torch op")
+        assert_close_f32(y, want, what=f"spmm_{op} forward vs reference torch op",
+                         absref=spmm_absref(oracle, case["rowptr"], case["col"], case["val"], case["B"], op))
 
 
-def test_sum_backward_same_as_reference_torch_op(case):
+def test_sum_backward_same_as_reference_torch_op(case, oracle):
     _, gval, gdense, _ = ours(case, "sum")
     assert "sum_gval" in case["ref"], case["ref"].get("sum_bwd_error")
-    assert_close_f32(gval, case["ref"]["sum_gval"], what="grad wrt values", scale=float(case["N"]) ** 0.5)
-    assert_close_f32(gdense, case["ref"]["sum_gdense"], what="grad wrt dense")
+    rowptr, col, val = case["rowptr"], case["col"], case["val"]
+    assert_close_f32(gval, case["ref"]["sum_gval"], what="grad wrt values",
+                     absref=sddmm_absref(oracle, rowptr, col, case["gout"], case["B"]))
+    colptr, row, val_t, _ = oracle.csr2csc(rowptr, col, val, ncols=case["M"])          # grad wrt dense = A^T gout
+    assert_close_f32(gdense, case["ref"]["sum_gdense"], what="grad wrt dense",
+                     absref=spmm_absref(oracle, colptr, row, val_t, case["gout"]))
 
 
 def test_csr2csc_same_as_reference_torch_op(case):
