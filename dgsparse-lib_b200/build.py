@@ -2,9 +2,12 @@
 
     python dgsparse-lib_b200/build.py [--force] [--verbose]
 
-Torch-free: every kernel and the C ABI live in csrc/*.cu; the PyTorch face binds the .so with ctypes.
-The SpMM kernel is compiled once per lane-group geometry (spmm_inst.cu with -DINST_VEC/-DINST_G) so
-the eight translation units build in parallel.
+Torch-free: every kernel and the C ABI live in csrc/*.cu.  The SpMM kernel is compiled once per lane-group geometry
+(spmm_inst.cu with -DINST_VEC/-DINST_G) so the translation units build in parallel.
+
+build_torch() then compiles the PyTorch operator boundary (host C++ only, no kernels) IN-TREE, the two files the
+reference ships (setup.py:26-84): dgsparse/_spmm_cuda.so (csrc/torch_ops.cpp: TORCH_LIBRARY(dgsparse_spmm) + autograd over
+the C ABI, loaded with torch.ops.load_library) and dgsparse/_C.so (csrc/version.cpp: pybind `cuda_version`).
 """
 import concurrent.futures as cf
 import os
@@ -80,5 +83,46 @@ def build(force=False, verbose=False):
     return LIB
 
 
+TORCH_OPS = os.path.join(HERE, "dgsparse", "_spmm_cuda.so")
+TORCH_C = os.path.join(HERE, "dgsparse", "_C.so")
+
+
+def build_torch(force=False, verbose=False):
+    """dgsparse/_spmm_cuda.so + dgsparse/_C.so with g++ against this interpreter's torch (needs libdgsparse_b200.so)."""
+    import sysconfig
+
+    import torch
+    tdir = os.path.dirname(torch.__file__)
+    abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
+    inc = [f"-I{tdir}/include", f"-I{tdir}/include/torch/csrc/api/include", "-I/usr/local/cuda/include",
+           f"-I{sysconfig.get_paths()['include']}"]
+    common = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", f"-D_GLIBCXX_USE_CXX11_ABI={abi}"] + inc
+    link = [f"-L{os.path.dirname(LIB)}", "-ldgsparse_b200", "-Wl,-rpath,$ORIGIN/../lib", f"-L{tdir}/lib", f"-Wl,-rpath,{tdir}/lib"]
+    jobs = [(TORCH_OPS, "torch_ops.cpp", ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
+                                          "-L/usr/local/cuda/lib64", "-lcudart"]),
+            (TORCH_C, "version.cpp", [])]
+    hdr = os.path.join(os.path.dirname(HERE), "include", "dgsparse_b200.h")
+    todo = []
+    for out, src, libs in jobs:
+        srcp = os.path.join(CSRC, src)
+        newest = max(os.path.getmtime(srcp), os.path.getmtime(hdr))
+        if force or not os.path.exists(out) or os.path.getmtime(out) < newest:
+            todo.append((out, common + [srcp, "-o", out] + link + libs))
+
+    def run(job):
+        out, cmd = job
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed for {out}:\n" + r.stdout + r.stderr)
+        if verbose:
+            print(f"[build] {out}")
+        return out
+    if todo:
+        with cf.ThreadPoolExecutor(max_workers=2) as ex:
+            list(ex.map(run, todo))
+    return TORCH_OPS, TORCH_C
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_torch(force="--force" in sys.argv, verbose=True))

@@ -158,6 +158,16 @@ int dgs_spmm_csr(int M, int N, int64_t nnz, const int *rowptr, const int *col, c
   return ok_or(dgs::spmm_csr(p, workspace, workspace_bytes, (cudaStream_t)stream), "dgs_spmm_csr");
 }
 
+int dgs_spmm_csr_k(int M, int K, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
+                   int64_t ldb, float *C, int64_t ldc, int *E, int64_t lde, int reduce, int compute, void *workspace,
+                   size_t workspace_bytes, void *stream) {
+  dgs::SpmmProblem p;
+  p.M = M; p.K = K; p.N = N; p.nnz = nnz; p.rowptr = rowptr; p.col = col; p.val = val; p.B = B; p.ldb = ldb;
+  p.n_dst = 1; p.dst[0] = C; p.ldc = ldc; p.E = E; p.lde = lde; p.reduce = reduce; p.compute = compute;
+  if (compute == DGS_MASKMUL) return fail(cudaErrorInvalidValue, "dgs_spmm_csr_k(compute): use dgs_spmm_csr_mask");
+  return ok_or(dgs::spmm_csr(p, workspace, workspace_bytes, (cudaStream_t)stream), "dgs_spmm_csr_k");
+}
+
 int dgs_spmm_csr_mask(int M, int N, int64_t nnz, const int *ptr, const int *idx, const float *val, const float *G,
                       int64_t ldg, const int *E, int64_t lde, float *out, int64_t ldo, void *workspace,
                       size_t workspace_bytes, void *stream) {
@@ -387,8 +397,8 @@ int dgs_spmm_csr_host(int M, int K, int N, int64_t nnz, const int *rowptr, const
     if ((e = cudaStreamWaitEvent(s_k, st.ev_in[b], 0)) != cudaSuccess) return fail(e, "event wait");
     if (rows > 0) {
       if (p0 != 0) rebase_rowptr_kernel<<<(rows + 1 + 255) / 256, 256, 0, s_k>>>(d_rp, rows + 1, (int)p0);
-      int rc = dgs_spmm_csr(rows, N, n, d_rp, d_col + p0, d_val ? d_val + p0 : nullptr, d_B, N, d_C + (size_t)r0 * N, N,
-                            d_E ? d_E + (size_t)r0 * N : nullptr, N, reduce, compute, d_ws, b_ws, s_k);
+      int rc = dgs_spmm_csr_k(rows, K, N, n, d_rp, d_col + p0, d_val ? d_val + p0 : nullptr, d_B, N, d_C + (size_t)r0 * N, N,
+                              d_E ? d_E + (size_t)r0 * N : nullptr, N, reduce, compute, d_ws, b_ws, s_k);
       if (rc) return rc;
     }
     if ((e = cudaEventRecord(st.ev_done[b], s_k)) != cudaSuccess) return fail(e, "event record");

@@ -106,15 +106,46 @@ static int pow2_at_least(int x, int lo, int hi) {
   return g;
 }
 
-// Lane-group geometry for feature width N.  vec4 needs 16-byte aligned rows everywhere.
-static void pick_geometry(int N, bool can_vec4, int *vec, int *G) {
+int device_l2_bytes() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 126 << 20;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrL2CacheSize, dev) != cudaSuccess || n <= 0) n = 126 << 20;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// Width (columns) of the B panel one pass over the nnz stream gathers from: 64 (16 lanes x float4), wider matrices run
+// as 64-column panels one after the other (blockIdx.y), so that the gathered panel, K rows x 256 B, is what has to stay
+// L2-resident, not all of B (measured on B200 against 128-column panels: reddit-like N=128 3.97 -> 3.29 ms, N=256
+// 8.66 -> 6.84 ms).
+// DEAD END, measured in round 2 (profiles/r02_exp_panels_*.jsonl, r02_ncu_panel_products128_*.csv, kernel kept under
+// tools/dead_ends/): narrower panels for operands that do not fit the L2 (products-like N=128: B = 1.25 GB).  32 / 16 / 8
+// columns: 9.2 / 20.4 / 43.1 ms against 8.65 ms at 64 — DRAM reads 57 -> 121 -> 249 GB, i.e. they DOUBLE per halving:
+// (1) the L2 is tagged per 128 B line, so a 32 B slice per 512 B row occupies a whole line and the "78 MB" panel needs 313 MB of
+// lines; a miss costs ~126 B of DRAM whatever the request size; (2) even fully resident (reddit-like N=128, 15 MB of
+// slices) the gather is bound by REQUESTS, not bytes: 141 / 171 / 183 G requests/s at 128 / 64 / 32 B per request, i.e.
+// 18 / 10.9 / 5.9 TB/s — a repacked contiguous 8-column panel would top out at 1.98 G requests / 183 G/s = 10.8 ms.
+// Only >= 128 B per request runs at full L2 rate.  DGS_SPMM_PANEL=32 keeps the 8-lane geometry reachable for experiments.
+static int pick_panel(int N, int64_t K, bool narrow_ok) {
+  (void)N; (void)K; (void)narrow_ok;
+  if (const char *e = getenv("DGS_SPMM_PANEL")) {
+    if (atoi(e) == 32) return 32;
+  }
+  return 64;
+}
+
+// Lane-group geometry for feature width N and panel width W.  vec4 needs 16-byte aligned rows everywhere.
+static void pick_geometry(int N, int W, bool can_vec4, int *vec, int *G, bool *narrow) {
+  *narrow = false;
   if (can_vec4) {
     *vec = 4;
-    // N=16 -> 4 lanes, 32 -> 8, >= 64 -> 16: wider matrices are processed as 64-column panels (blockIdx.y), one
-    // panel after the other, so the gathered B panel (K x 256 B) is what has to stay L2-resident, not the whole
-    // of B.  Measured on B200 against 128-column panels (32 lanes): reddit-like N=128 3.97 -> 3.29 ms, N=256
-    // 8.66 -> 6.84 ms; products-like (B >> L2 either way) 9.09 -> 8.80 ms and 18.06 -> 17.81 ms.
+    // N=16 -> 4 lanes, 32 -> 8, >= 64 -> 16 lanes x float4; a narrower panel only when the matrix is wider than it
     *G = pow2_at_least((N + 3) / 4, 4, 16);
+    if (W < 64 && N > W) *G = W / 4;
   } else {
     *vec = 1;
     *G = pow2_at_least(N, 4, 32);
@@ -164,20 +195,22 @@ static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static void geometry_for(int N, int64_t nnz, bool with_arg, bool can_vec4, int *vec, int *G, int *chunk,
-                         int *num_chunks) {
-  pick_geometry(N, can_vec4, vec, G);
+static void geometry_for(int N, int64_t nnz, bool with_arg, bool can_vec4, int W, int *vec, int *G, bool *narrow,
+                         int *chunk, int *num_chunks) {
+  pick_geometry(N, W, can_vec4, vec, G, narrow);
   *chunk = pick_chunk(N, nnz, with_arg, *G);
   *num_chunks = (int)((nnz + *chunk - 1) / *chunk);
 }
 
 size_t spmm_workspace_bytes(int N, int64_t nnz, bool with_arg) {
   if (nnz <= 0 || N <= 0) return 256;
-  // the segment length differs between the vec4 and scalar geometries; size for the larger need
+  // the segment length differs between the geometries (vec4 at every panel width, scalar); size for the largest need
   size_t need = 0;
-  for (int pass = 0; pass < 2; pass++) {
+  for (int pass = 0; pass < 3; pass++) {
+    static const int widths[3] = {64, 32, 64};
     int vec, G, chunk, nc;
-    geometry_for(N, nnz, with_arg, pass == 0, &vec, &G, &chunk, &nc);
+    bool narrow;
+    geometry_for(N, nnz, with_arg, pass < 2, widths[pass], &vec, &G, &narrow, &chunk, &nc);
     size_t b = align_up((size_t)nc * 4, 256) + align_up((size_t)nc * 2 * N * 4, 256) * (with_arg ? 2 : 1);
     if (b > need) need = b;
   }
@@ -210,10 +243,12 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   for (int d = 0; d < kMaxDst; d++) a.dst[d] = d < p.n_dst ? p.dst[d] : nullptr;
 
   int vec = 1, G = 32;
+  bool narrow = false;
   a.chunk = kBatch; a.num_chunks = 0;
   a.part_val = nullptr; a.part_arg = nullptr; a.tail_row = nullptr;
   if (p.nnz > 0) {
-    geometry_for(p.N, p.nnz, with_arg, can_vec4, &vec, &G, &a.chunk, &a.num_chunks);
+    const int W = pick_panel(p.N, p.K > 0 ? p.K : p.M, false);
+    geometry_for(p.N, p.nnz, with_arg, can_vec4, W, &vec, &G, &narrow, &a.chunk, &a.num_chunks);
     const size_t tail_b = align_up((size_t)a.num_chunks * 4, 256);
     const size_t part_b = align_up((size_t)a.num_chunks * 2 * p.N * 4, 256);
     const size_t need = tail_b + part_b * (with_arg ? 2 : 1);

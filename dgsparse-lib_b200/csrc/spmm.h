@@ -8,6 +8,7 @@ namespace dgs {
 
 struct SpmmProblem {
   int M = 0, N = 0;
+  int K = 0;                    // rows of B (columns of A); 0 = unknown, taken as M (square adjacency).  Only sizes the column panels.
   int64_t nnz = 0;
   const int *rowptr = nullptr;
   const int *col = nullptr;

@@ -44,9 +44,9 @@ def spmm(rowptr, col, values, dense, reduce=_lib.SUM, compute=_lib.MUL, with_arg
             return (out, E) if with_arg else out
         ws_bytes = lib.dgs_spmm_workspace_bytes(N, nnz, int(with_arg))
         ws = _workspace(ws_bytes, dense.device)
-        check(lib.dgs_spmm_csr(M, N, nnz, ptr(rowptr), ptr(col), ptr(values), ptr(dense), dense.stride(0),
-                               ptr(out), out.stride(0), ptr(E), N if with_arg else 0, int(reduce), int(compute),
-                               ptr(ws), ws.numel(), stream_of(dense)), "dgs_spmm_csr")
+        check(lib.dgs_spmm_csr_k(M, dense.size(0), N, nnz, ptr(rowptr), ptr(col), ptr(values), ptr(dense), dense.stride(0),
+                                 ptr(out), out.stride(0), ptr(E), N if with_arg else 0, int(reduce), int(compute),
+                                 ptr(ws), ws.numel(), stream_of(dense)), "dgs_spmm_csr_k")
     return (out, E) if with_arg else out
 
 

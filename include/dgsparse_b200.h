@@ -40,6 +40,12 @@ size_t dgs_spmm_workspace_bytes(int N, int64_t nnz, int with_arg);
 int dgs_spmm_csr(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
                  int64_t ldb, float *C, int64_t ldc, int *E, int64_t lde, int reduce, int compute, void *workspace,
                  size_t workspace_bytes, void *stream);
+/* The same with K = rows of B (columns of A) stated.  K only sizes the column panels (csrc/spmm.cu pick_panel): when a
+ * 64-column panel of B, K x 256 B, would not stay L2-resident the feature axis is processed in narrower panels, one after
+ * the other.  dgs_spmm_csr takes K = M (square adjacency). */
+int dgs_spmm_csr_k(int M, int K, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
+                   int64_t ldb, float *C, int64_t ldc, int *E, int64_t lde, int reduce, int compute, void *workspace,
+                   size_t workspace_bytes, void *stream);
 int dgs_spmm_csr_multi(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
                        int64_t ldb, int n_dst, float *const *dst, int64_t ldc, int reduce, int compute, void *workspace,
                        size_t workspace_bytes, void *stream);

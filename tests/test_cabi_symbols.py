@@ -69,3 +69,42 @@ def test_ops_fail_loudly_without_cuda():
     col = torch.tensor([0], dtype=torch.int32)
     with pytest.raises(RuntimeError, match="no CPU path"):
         K.spmm(rowptr, col, None, torch.ones(1, 4))
+
+
+def test_compiled_op_library_loads_without_the_python_package():
+    """The reference's boundary is a loadable op library (dgsparse/_spmm_cuda.so + torch.ops.load_library,
+    dgsparse/__init__.py:16-26; TORCH_LIBRARY at src/spmm.cpp:264-270).  Ours (csrc/torch_ops.cpp) must load in a FRESH
+    interpreter that never imports the dgsparse package or its Python op registration, and expose the same five ops with
+    the schemas the reference's C++ signatures imply; on CPU tensors they fail loudly (no CPU path)."""
+    import subprocess
+    import sys
+    import __graft_entry__
+    __graft_entry__.build()
+    so = os.path.join(ROOT, "dgsparse-lib_b200", "dgsparse", "_spmm_cuda.so")
+    assert os.path.exists(so)
+    code = f"""
+import sys, torch
+torch.ops.load_library({so!r})
+assert 'dgsparse' not in sys.modules and 'dgsparse._ops' not in sys.modules
+want = "(Tensor _0, Tensor _1, Tensor _2, Tensor _3, Tensor _4, Tensor _5, Tensor _6, bool _7, int _8) -> Tensor _0"
+for op in ("spmm_sum", "spmm_max", "spmm_min", "spmm_mean"):
+    s = str(getattr(torch.ops.dgsparse_spmm, op).default._schema)
+    assert s == "dgsparse_spmm::" + op + want, s
+assert str(torch.ops.dgsparse_spmm.csr2csc.default._schema) == "dgsparse_spmm::csr2csc(Tensor _0, Tensor _1, Tensor _2) -> Tensor[] _0"
+i = lambda *v: torch.tensor(v, dtype=torch.int32)
+try:
+    torch.ops.dgsparse_spmm.spmm_sum(i(0, 1), i(0), torch.ones(1), i(0, 1), i(0), i(0), torch.ones(1, 4), True, 0)
+except RuntimeError as e:
+    assert "no CPU path" in str(e), e
+else:
+    raise SystemExit("CPU tensors did not raise")
+print("ok")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+
+
+def test_package_uses_the_compiled_ops_by_default():
+    import dgsparse
+    assert dgsparse.ops_backend.startswith("compiled"), dgsparse.ops_backend
+    assert dgsparse._C.__file__.endswith("_C.so")

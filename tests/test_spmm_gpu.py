@@ -241,3 +241,74 @@ def test_full_size_properties(K, graphs):
         ref = (val[s:e].double()[:, None] * B[cc[s:e].long()].double()).sum(0)
         assert torch.allclose(C[r].double(), ref, rtol=1e-5, atol=0.0), r   # inputs >= 0: purely relative
     assert torch.equal(C, K.spmm(rp, cc, val, B))
+
+
+@pytest.mark.parametrize("panel", ["32"])
+@pytest.mark.parametrize("N", [16, 64, 100, 128, 136, 256])
+def test_narrow_panels_same_as_wide(K, oracle, graphs, monkeypatch, panel, N):
+    """Column panels narrower than 64 (DGS_SPMM_PANEL=32: the 8-lane row-segment geometry on matrices wider than its panel;
+    the 8 / 16-column kernels were a measured dead end, csrc/spmm.cu pick_panel).  Every reduce, with and without edge
+    values; max / min and their arg index bit-exact, sum / mean within the stated tolerance (segment boundaries, hence the
+    places where a long row's partial sums are folded, differ with the group width, so sums are not bit-identical across
+    panel widths)."""
+    M, Kc = 4000, 3500
+    rowptr, col = graphs.random_csr(M, Kc, 130000, 300 + N, empty_frac=0.25, hub=2)
+    val = graphs.uniform(col.size, 1, 0.5, 1.5)
+    B = graphs.uniform(Kc * N, 2, -1.0, 1.0).reshape(Kc, N)
+    d = [dev(rowptr), dev(col), dev(val), dev(B)]
+    for reduce in ("sum", "mean", "max", "min"):
+        for v in (d[2], None):
+            wa = reduce in ("max", "min")
+            monkeypatch.setenv("DGS_SPMM_PANEL", panel)
+            got = K.spmm(d[0], d[1], v, d[3], RED[reduce], COMP["mul"], with_arg=wa)
+            hv = None if v is None else val
+            if wa:
+                ref, Eref = oracle.spmm(rowptr, col, hv, B, reduce, "mul", with_arg=True)
+                assert np.array_equal(got[0].cpu().numpy(), ref) and np.array_equal(got[1].cpu().numpy(), Eref)
+            else:
+                assert_close_f32(got.cpu().numpy(), oracle.spmm(rowptr, col, hv, B, reduce), oracle.spmm_f64(rowptr, col, hv, B, reduce),
+                                 what=f"panel {panel} N={N} {reduce}", absref=spmm_absref(oracle, rowptr, col, hv, B, reduce))
+
+
+def test_products_like_full_size(K, oracle, graphs):
+    """BASELINE config 3 at full size: products-like CSR (2 449 029 rows, 123.7 M nnz), feat 128, the gspmm-fp ops
+    copy_u_max / copy_u_mean / u_mul_e_max / u_mul_e_mean (example/gspmm-fp/util.py); B (1.25 GB) is 10x the L2.  Checks: (1) identity with the reference's own gspmm-fp module where it
+    was built (max bit-identical, mean 1e-5), (2) ~200 sampled rows incl. the 8 longest against fp64, (3) determinism."""
+    import dgsparse.gspmm as G
+    rowptr, col = graphs.products_like(1.0)
+    M, nnz, N = rowptr.size - 1, col.size, 128
+    rp, cc = dev(rowptr), dev(col)
+    val = torch.rand(nnz, device="cuda", generator=torch.Generator("cuda").manual_seed(1)) + 0.5
+    B = torch.rand(M, N, device="cuda", generator=torch.Generator("cuda").manual_seed(2)) * 2 - 1
+    REF = oracle.ref_gspmm_module()
+    rows = np.unique(np.concatenate([np.arange(0, M, M // 190), np.argsort(np.diff(rowptr))[-8:]]))
+    for name in ("copy_u_max", "copy_u_mean", "u_mul_e_max", "u_mul_e_mean"):
+        red = name.rsplit("_", 1)[1]
+        has_val = name.startswith("u_mul")
+        out = getattr(G, name)(rp, cc, val.reshape(-1, 1), B) if has_val else getattr(G, name)(rp, cc, B)
+        assert tuple(out.shape) == (M, N)
+        if REF is not None:
+            theirs = (REF.GSpMM_u_e(rp, cc, val, B, getattr(REF.REDUCEOP, red.upper()), REF.COMPUTEOP.MUL) if has_val
+                      else REF.GSpMM_u(rp, cc, B, getattr(REF.REDUCEOP, red.upper())))
+            if red == "max":
+                assert torch.equal(out, theirs), name
+            else:   # two fp32 means of ~50 signed terms: compare both to fp64 below, and each other loosely relative to |terms|
+                assert torch.allclose(out, theirs, rtol=1e-5, atol=1e-5), name
+            del theirs
+        for r in rows:
+            s, e = int(rowptr[r]), int(rowptr[r + 1])
+            if e == s:
+                assert (out[r] == 0).all()
+                continue
+            t32 = B[cc[s:e].long()]
+            if has_val:
+                t32 = t32 * val[s:e][:, None]                      # one correctly rounded fp32 product per term, as the kernel
+            terms = t32.double()
+            if red == "max":
+                assert torch.equal(out[r], t32.max(0).values), (name, int(r))
+            else:
+                want, mag = terms.mean(0), terms.abs().mean(0)
+                assert ((out[r].double() - want).abs() <= 1e-5 * want.abs() + 1e-6 * mag).all(), (name, int(r))
+        again = getattr(G, name)(rp, cc, val.reshape(-1, 1), B) if has_val else getattr(G, name)(rp, cc, B)
+        assert torch.equal(out, again), name
+        del out, again

@@ -159,8 +159,8 @@ def test_forward_same_as_reference_on_minkunet_fixture(REF, idx, arch80):
     theirs = ref_forward(REF, dx, dw, kpos, qkpos, di, do, out_nnz, sum_nnz, False, arch80).cpu().numpy()
     ours = S.spconv_fwd_fused(dx, dw, kpos, qkpos, di, do, out_nnz, sum_nnz, False, arch80).cpu().numpy()
     want, bound = ref64(g["kpos"], g["imap"], g["omap"], x, w, out_nnz)
-    # the reference's small-channel kernel (c_in <= 16) is plain fp32 whatever arch80 says (spconv_cuda.cu:136-144)
-    prec_ref = "tf32" if (arch80 and c_in > 16) else "fp32"
+    # the reference's small-channel kernel (c_in <= 16 AND c_out <= 16) is plain fp32 whatever arch80 says (spconv_cuda.cu:136-144)
+    prec_ref = "tf32" if (arch80 and not (c_in <= 16 and c_out <= 16)) else "fp32"
     prec = "tf32" if arch80 else "fp32"
     check(theirs, want, bound, prec_ref, f"reference fixture {idx}")
     check(ours, want, bound, prec, f"ours fixture {idx}")
