@@ -60,9 +60,46 @@ void legacy_report(int rc, const char *fn) {
   if (rc != 0) fprintf(stderr, "[dgsparse_b200] %s failed: %s\n", fn, g_err);
 }
 
-// nnz of a device CSR when the caller does not pass it (legacy spmm_cuda): rowptr[m] via a 4-byte copy.
-cudaError_t read_nnz(const int *rowptr, int m, int *nnz) {
-  return cudaMemcpy(nnz, rowptr + m, sizeof(int), cudaMemcpyDeviceToHost);
+// nnz of a device CSR when the caller does not pass it (legacy spmm_cuda(m, k, rowptr, ...)).  The reference never needs
+// it (src/ge-spmm/gespmm.cc:114-129 is fully asynchronous); our segment scheme does, to size the grid.  A blocking 4-byte
+// copy of rowptr[m] on every call would serialise the caller's stream, so it happens ONCE per (device, rowptr, m): later
+// calls size the grid from a hint — the nnz the kernels themselves found last time, reported through a mapped host word —
+// and the kernels re-derive the segment layout from the true rowptr[m] on the device (seg_layout, spmm_rowseg.cuh), so
+// a CSR rewritten in place under the same pointer still gives the right answer, only with a stale grid size for one call.
+struct NnzHint {
+  const int *rowptr = nullptr;
+  int m = -1, dev = -1, nnz = -1;
+  int *mail_host = nullptr, *mail_dev = nullptr;   // mapped pinned word, allocated once per slot
+};
+NnzHint g_hints[32];
+int g_hint_clock = 0;
+
+// -> hint nnz (> 0) and the device address of the report word; hint <= 0: the caller must not use the hinted path
+cudaError_t legacy_nnz_hint(const int *rowptr, int m, int *nnz, int **report) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(g_mu);
+  NnzHint *h = nullptr;
+  for (auto &c : g_hints)
+    if (c.rowptr == rowptr && c.m == m && c.dev == dev) { h = &c; break; }
+  if (h == nullptr) {
+    h = &g_hints[g_hint_clock++ % 32];
+    if (h->mail_host == nullptr) {
+      if ((e = cudaHostAlloc((void **)&h->mail_host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable)) != cudaSuccess) return e;
+      if ((e = cudaHostGetDevicePointer((void **)&h->mail_dev, h->mail_host, 0)) != cudaSuccess) return e;
+    }
+    *(volatile int *)h->mail_host = -1;
+    h->rowptr = rowptr; h->m = m; h->dev = dev;
+    if ((e = cudaMemcpy(&h->nnz, rowptr + m, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) { h->rowptr = nullptr; return e; }   // first sight only
+  } else {
+    const int seen = *(volatile int *)h->mail_host;   // whatever the latest finished call found; no synchronisation
+    if (seen >= 0) h->nnz = seen;
+    if (h->nnz <= 0 && (e = cudaMemcpy(&h->nnz, rowptr + m, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) return e;
+  }
+  *nnz = h->nnz;
+  *report = h->mail_dev;
+  return cudaSuccess;
 }
 
 // ---- column-major SpMM (gespmmCsrSpMM with transpose_BC = false) ---------------------------------
@@ -120,6 +157,7 @@ int dgs_version(void) { return 100; }
 int dgs_cuda_version(void) { return CUDA_VERSION; }
 const char *dgs_last_error(void) { return g_err; }
 int dgs_sm_count(void) { return dgs::device_sm_count(); }
+int dgs_spmm_last_path(void) { return dgs::spmm_last_path(); }
 
 size_t dgs_spmm_workspace_bytes(int N, int64_t nnz, int with_arg) {
   return dgs::spmm_workspace_bytes(N, nnz, with_arg != 0);
@@ -471,11 +509,6 @@ int dgs_profile_collect(int max_records, int *kernel_ids, float *ms) { return dg
 
 void gespmmCsrSpMM(const SpMatCsrDescr_t A, float *B, const int N, float *C, bool transpose_BC, gespmmAlg_t alg) {
   (void)alg;  // every reference algorithm computes the same C; one kernel serves them all
-  int nnz = A.nnz;
-  if (nnz < 0) {
-    cudaError_t e = read_nnz(A.indptr, A.nrow, &nnz);
-    if (e != cudaSuccess) { legacy_report(fail(e, "gespmmCsrSpMM(read nnz)"), "gespmmCsrSpMM"); return; }
-  }
   if (!transpose_BC) {
     if (A.nrow <= 0 || N <= 0) return;
     dim3 grid((A.nrow + 255) / 256, N);
@@ -483,12 +516,21 @@ void gespmmCsrSpMM(const SpMatCsrDescr_t A, float *B, const int N, float *C, boo
     legacy_report(ok_or(cudaGetLastError(), "gespmmCsrSpMM(colmajor)"), "gespmmCsrSpMM");
     return;
   }
-  const size_t need = dgs::spmm_workspace_bytes(N, nnz, false);
+  dgs::SpmmProblem p;
+  p.M = A.nrow; p.K = A.ncol; p.N = N; p.nnz = A.nnz; p.rowptr = A.indptr; p.col = A.indices; p.val = A.data; p.B = B; p.ldb = N;
+  p.n_dst = 1; p.dst[0] = C; p.ldc = N; p.reduce = dgs::R_SUM; p.compute = dgs::C_MUL;
+  if (A.nnz < 0) {   // spmm_cuda(m, k, rowptr, ...): nnz lives on the device, the host only has a hint (see legacy_nnz_hint)
+    int hint = 0, *report = nullptr;
+    cudaError_t e = legacy_nnz_hint(A.indptr, A.nrow, &hint, &report);
+    if (e != cudaSuccess) { legacy_report(fail(e, "gespmmCsrSpMM(nnz hint)"), "gespmmCsrSpMM"); return; }
+    p.nnz = hint;
+    if (hint > 0) { p.nnz_on_device = true; p.nnz_report = report; }
+  }
+  const size_t need = dgs::spmm_workspace_bytes(N, p.nnz, false);
   void *ws = nullptr;
   cudaError_t e = legacy_scratch(need, &ws);
   if (e != cudaSuccess) { legacy_report(fail(e, "gespmmCsrSpMM(scratch)"), "gespmmCsrSpMM"); return; }
-  legacy_report(dgs_spmm_csr(A.nrow, N, nnz, A.indptr, A.indices, A.data, B, N, C, N, nullptr, 0, DGS_SUM, DGS_MUL, ws,
-                             need, nullptr), "gespmmCsrSpMM");
+  legacy_report(ok_or(dgs::spmm_csr(p, ws, need, nullptr), "gespmmCsrSpMM"), "gespmmCsrSpMM");
 }
 
 // ---- the older SpMV/SpMM API (src/ge-spmm/gespmm_v2.h) ----------------------------------------------

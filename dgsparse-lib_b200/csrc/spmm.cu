@@ -4,14 +4,19 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <mutex>
 #include "spmm.h"
 #include "spmm_rowseg.cuh"
+#include "spmm_rowpar.cuh"
 
 namespace dgs {
 
 #define DGS_DECL_LOOKUP(V, G) SpmmLaunchFn spmm_lookup_v##V##_g##G(int red, int comp, bool arg);
 DGS_DECL_LOOKUP(4, 4) DGS_DECL_LOOKUP(4, 8) DGS_DECL_LOOKUP(4, 16) DGS_DECL_LOOKUP(4, 32)
 DGS_DECL_LOOKUP(1, 4) DGS_DECL_LOOKUP(1, 8) DGS_DECL_LOOKUP(1, 16) DGS_DECL_LOOKUP(1, 32)
+SpmmLaunchFn spmm_rowpar_lookup_v4_g4(int red, int comp, bool arg);
+SpmmLaunchFn spmm_rowpar_lookup_v4_g8(int red, int comp, bool arg);
+SpmmLaunchFn spmm_rowpar_lookup_v4_g16(int red, int comp, bool arg);
 
 // pdl: the fix-up grid is a programmatic dependent of the SpMM grid launched just before it on the same stream — it may
 // start while that grid runs (its empty-row half is independent) and waits for it with griddepcontrol.wait.
@@ -97,6 +102,82 @@ int device_sm_count() {
   }
   return cached[dev];
 }
+
+// ---- graph notes: which matrices may take the single-launch row-parallel kernel -------------------------------------
+// The row-parallel kernel (spmm_rowpar.cuh) wins in the latency regime but walks a row serially, so it needs to know that
+// the matrix has no long row — which neither C ABI tells us.  The library therefore remembers, per (device, rowptr, M),
+// what its own kernels saw: the first call on a matrix takes the segment path, whose fix-up grid scans every row anyway
+// and sets a mapped host word when one exceeds kRowParLimit; an event marks the end of that scan.  Later calls read the
+// word WITHOUT synchronising (cudaEventQuery) and switch to the row-parallel kernel if it stayed clear.  The note is only
+// a hint: the row-parallel kernel is correct for any matrix and raises the same word when it meets a long row (a CSR
+// rewritten in place under the same pointer), which sends the following calls back to the segment path.
+namespace {
+constexpr int64_t kRowParMaxNnz = 4 << 20;
+struct GraphNote {
+  const int *rowptr = nullptr;
+  int m = -1, dev = -1;
+  int verdict = -1;      // -1 unknown, 0 no row longer than kRowParLimit, 1 has long rows
+  bool pending = false;  // a full scan is enqueued; `ev` marks its end
+  cudaEvent_t ev = nullptr;
+  int *flag_host = nullptr, *flag_dev = nullptr;
+};
+std::mutex g_note_mu;
+GraphNote g_notes[32];
+int g_note_clock = 0;
+
+thread_local int g_last_path = 0;   // 0 = row-segment kernel + fix-up, 1 = row-parallel single launch
+
+int rowpar_mode() {   // DGS_SPMM_ROWPAR: 0 = never, 1 = always (tests), unset = by graph note
+  const char *e = getenv("DGS_SPMM_ROWPAR");
+  return e ? (atoi(e) ? 1 : 0) : -1;
+}
+
+// -> index of the note (creating it on first sight), or -1
+int note_lookup(const int *rowptr, int m, int *verdict, int **flag_dev, bool *want_scan) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  std::lock_guard<std::mutex> lk(g_note_mu);
+  int idx = -1;
+  for (int i = 0; i < 32; i++)
+    if (g_notes[i].rowptr == rowptr && g_notes[i].m == m && g_notes[i].dev == dev) { idx = i; break; }
+  if (idx < 0) {
+    idx = g_note_clock++ % 32;
+    GraphNote &n = g_notes[idx];
+    if (n.flag_host == nullptr) {
+      if (cudaHostAlloc((void **)&n.flag_host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+          cudaHostGetDevicePointer((void **)&n.flag_dev, n.flag_host, 0) != cudaSuccess ||
+          cudaEventCreateWithFlags(&n.ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        n.flag_host = nullptr; n.rowptr = nullptr;
+        return -1;
+      }
+    }
+    *(volatile int *)n.flag_host = 0;
+    n.rowptr = rowptr; n.m = m; n.dev = dev; n.verdict = -1; n.pending = false;
+  }
+  GraphNote &n = g_notes[idx];
+  if (n.pending) {
+    const cudaError_t q = cudaEventQuery(n.ev);
+    if (q == cudaSuccess) { n.pending = false; n.verdict = *(volatile int *)n.flag_host ? 1 : 0; }
+    else cudaGetLastError();   // cudaErrorNotReady is not an error
+  } else if (n.verdict == 0 && *(volatile int *)n.flag_host) {
+    n.verdict = 1;             // a row-parallel launch met a long row: the matrix changed under this pointer
+  }
+  *verdict = n.verdict;
+  *flag_dev = n.flag_dev;
+  *want_scan = n.verdict < 0 && !n.pending;
+  return idx;
+}
+
+void note_scan_enqueued(int idx, const int *rowptr, cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_note_mu);
+  GraphNote &n = g_notes[idx];
+  if (n.rowptr != rowptr) return;   // recycled meanwhile
+  if (cudaEventRecord(n.ev, s) == cudaSuccess) n.pending = true;
+}
+}  // namespace
+
+int spmm_last_path() { return g_last_path; }
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -237,6 +318,8 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   a.E = p.E; a.lde = p.lde;
   a.mask = p.mask; a.ldm = p.ldm;
   a.mean = (p.reduce == R_MEAN);
+  a.nnz_dev = p.nnz_on_device ? 1 : 0;
+  a.nnz_report = p.nnz_report;
   a.n_dst = p.n_dst;
   a.mcast = p.mcast;
   if (p.mcast && p.n_dst != 1) return cudaErrorInvalidValue;
@@ -246,6 +329,32 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   bool narrow = false;
   a.chunk = kBatch; a.num_chunks = 0;
   a.part_val = nullptr; a.part_arg = nullptr; a.tail_row = nullptr;
+  a.hub_flag = nullptr; a.hub_limit = kRowParLimit;
+
+  // latency regime: single-launch row-parallel kernel when this matrix is known to have short rows only
+  int note = -1;
+  bool want_scan = false;
+  const int rp_mode = rowpar_mode();
+  if (p.nnz > 0 && p.nnz <= kRowParMaxNnz && can_vec4 && (comp == C_MUL || comp == C_COPY) && rp_mode != 0) {
+    int verdict = -1, *flag_dev = nullptr;
+    note = note_lookup(p.rowptr, p.M, &verdict, &flag_dev, &want_scan);
+    if (note >= 0) a.hub_flag = flag_dev;
+    if ((note >= 0 && verdict == 0) || rp_mode == 1) {
+      pick_geometry(p.N, 64, true, &vec, &G, &narrow);
+      SpmmLaunchFn fn = G == 4 ? spmm_rowpar_lookup_v4_g4(p.reduce, comp, with_arg)
+                      : G == 8 ? spmm_rowpar_lookup_v4_g8(p.reduce, comp, with_arg)
+                               : spmm_rowpar_lookup_v4_g16(p.reduce, comp, with_arg);
+      if (fn != nullptr) {
+        const int gpb = kSpmmThreads / G;
+        dim3 grid((p.M + gpb - 1) / gpb, (p.N + G * vec - 1) / (G * vec));
+        ProfileScope prof(1, stream);
+        g_last_path = 1;
+        return fn(a, grid, stream);
+      }
+    }
+    if (!want_scan) a.hub_flag = nullptr;   // the segment path only reports while the note is still open
+  }
+  g_last_path = 0;
   if (p.nnz > 0) {
     const int W = pick_panel(p.N, p.K > 0 ? p.K : p.M, false);
     geometry_for(p.N, p.nnz, with_arg, can_vec4, W, &vec, &G, &narrow, &a.chunk, &a.num_chunks);
@@ -287,10 +396,16 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   const int blocks = (int)((threads + 255) / 256);
   // dependent launch only right behind the SpMM grid, and not while the bench brackets the two launches with events
   const bool pdl = p.nnz > 0 && !profile_is_on() && !getenv("DGS_SPMM_NO_PDL");
-  ProfileScope prof(2, stream);
-  if (can_vec4)
-    return with_arg ? launch_fixup<true, 4>(p.reduce, a, blocks, pdl, stream) : launch_fixup<false, 4>(p.reduce, a, blocks, pdl, stream);
-  return with_arg ? launch_fixup<true, 1>(p.reduce, a, blocks, pdl, stream) : launch_fixup<false, 1>(p.reduce, a, blocks, pdl, stream);
+  cudaError_t fe;
+  {
+    ProfileScope prof(2, stream);
+    if (can_vec4)
+      fe = with_arg ? launch_fixup<true, 4>(p.reduce, a, blocks, pdl, stream) : launch_fixup<false, 4>(p.reduce, a, blocks, pdl, stream);
+    else
+      fe = with_arg ? launch_fixup<true, 1>(p.reduce, a, blocks, pdl, stream) : launch_fixup<false, 1>(p.reduce, a, blocks, pdl, stream);
+  }
+  if (fe == cudaSuccess && note >= 0 && want_scan && a.hub_flag != nullptr) note_scan_enqueued(note, p.rowptr, stream);   // the fix-up grid scanned every row
+  return fe;
 }
 
 }  // namespace dgs

@@ -25,11 +25,17 @@ struct SpmmProblem {
   int compute = 2;              // dgs::ComputeOp (C_MUL)
   const int *mask = nullptr;    // compute == C_MASK: the forward's arg tensor, row stride ldm
   int64_t ldm = 0;
+  // Legacy entry points without an nnz argument: `nnz` above is only a HINT (what rowptr[M] held on an earlier call); the
+  // kernels read the true value on the device and re-derive the segment layout, and report it into *nnz_report (mapped
+  // host memory, may be null) for the next call.  No device->host copy, no synchronisation.
+  bool nnz_on_device = false;
+  int *nnz_report = nullptr;
 };
 
 size_t spmm_workspace_bytes(int N, int64_t nnz, bool with_arg);
 cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int device_sm_count();
+int spmm_last_path();   // which kernel family the calling thread's last spmm_csr launched: 0 row-segment (+ fix-up), 1 row-parallel
 
 // bench-only launch timing (see dgs_profile_enable in include/dgsparse_b200.h)
 int profile_enable(bool on);

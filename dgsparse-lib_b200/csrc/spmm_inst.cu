@@ -2,6 +2,7 @@
 // (REDUCE, COMPUTE, ARG) flavour of spmm_rowseg_kernel for that lane-group geometry and exports a
 // lookup function the dispatcher in spmm.cu uses.
 #include "spmm_rowseg.cuh"
+#include "spmm_rowpar.cuh"
 
 #ifndef INST_VEC
 #error "compile with -DINST_VEC=<1|4> -DINST_G=<4|8|16|32>"
@@ -41,5 +42,26 @@ SpmmLaunchFn DGS_LOOKUP(int red, int comp, bool arg) {
   default: return nullptr;
   }
 }
+
+// Row-parallel single-launch kernels (spmm_rowpar.cuh): the 16-byte geometries only, multiply / no-edge-value.
+#if INST_VEC == 4 && INST_G <= 16
+#define DGS_ROWPAR_LOOKUP DGS_CAT(spmm_rowpar_lookup_v, INST_VEC, _g, INST_G)
+template <int RED, bool ARG> static SpmmLaunchFn rowpar_by_comp(int comp) {
+  switch (comp) {
+  case C_MUL: return &launch_spmm_rowpar<INST_VEC, INST_G, RED, C_MUL, ARG>;
+  case C_COPY: return &launch_spmm_rowpar<INST_VEC, INST_G, RED, C_COPY, ARG>;
+  default: return nullptr;
+  }
+}
+SpmmLaunchFn DGS_ROWPAR_LOOKUP(int red, int comp, bool arg) {
+  switch (red) {
+  case R_SUM:
+  case R_MEAN: return arg ? nullptr : rowpar_by_comp<R_SUM, false>(comp);
+  case R_MAX: return arg ? rowpar_by_comp<R_MAX, true>(comp) : rowpar_by_comp<R_MAX, false>(comp);
+  case R_MIN: return arg ? rowpar_by_comp<R_MIN, true>(comp) : rowpar_by_comp<R_MIN, false>(comp);
+  default: return nullptr;
+  }
+}
+#endif
 
 }  // namespace dgs

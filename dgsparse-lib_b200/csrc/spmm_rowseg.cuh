@@ -51,7 +51,28 @@ struct SpmmArgs {
   float *dst[kMaxDst];
   const int *mask;    // COMP == C_MASK only: arg index tensor E of the forward, [*, ldm]
   int64_t ldm;
+  int nnz_dev;        // the true nnz is rowptr[M] ON THE DEVICE; nnz / chunk / num_chunks above come from a host-side hint
+  int *nnz_report;    // (with nnz_dev) mapped host word that receives the true nnz: the next call's hint
+  int *hub_flag;      // mapped host word set to 1 when a row longer than kRowParLimit is seen (null: nobody asks)
+  int hub_limit;
 };
+
+// Segment layout actually used by a launch.  Normally the host's (a.nnz, a.chunk, a.num_chunks).  The legacy entry points
+// (spmm_cuda(m, k, rowptr, ...): no nnz argument) must not block on a device->host copy of rowptr[M], so there the host
+// sizes the grid and the workspace from the nnz it saw on the previous call with this rowptr (a hint) and every kernel
+// re-derives the layout from the true nnz: same segments when the hint was right, fewer when nnz shrank, LONGER segments
+// (never more than the a.num_chunks the workspace was sized for) when it grew.
+struct SegLayout { int nnz, chunk, num_chunks; };
+__device__ __forceinline__ SegLayout seg_layout(const SpmmArgs &a) {
+  SegLayout s = {a.nnz, a.chunk, a.num_chunks};
+  if (a.nnz_dev) {
+    s.nnz = __ldg(a.rowptr + a.M);
+    const int need = (int)(((int64_t)s.nnz + a.num_chunks - 1) / a.num_chunks);
+    if (need > s.chunk) s.chunk = (need + 31) / 32 * 32;
+    s.num_chunks = (int)(((int64_t)s.nnz + s.chunk - 1) / s.chunk);
+  }
+  return s;
+}
 
 constexpr int kSpmmThreads = 256;
 constexpr int kBatch = 32;
@@ -96,10 +117,11 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
   // nothing this kernel reads or writes, its second half waits for this grid (griddepcontrol.wait).
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int chunk_id = blockIdx.x * GPB + grp;
-  if (chunk_id >= a.num_chunks) return;
+  const SegLayout sl = seg_layout(a);
+  if (chunk_id >= sl.num_chunks) return;
 
-  const int lo = chunk_id * a.chunk;
-  const int hi = (a.nnz - lo <= a.chunk) ? a.nnz : lo + a.chunk;
+  const int lo = chunk_id * sl.chunk;
+  const int hi = (sl.nnz - lo <= sl.chunk) ? sl.nnz : lo + sl.chunk;
   const int colbase = blockIdx.y * (G * VEC) + gl * VEC;
   const bool active = colbase < a.N;
   // lanes beyond a ragged N recompute panel 0 (always in bounds) and never store: no predication in the hot loop
@@ -274,7 +296,11 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
   if (row0 < a.M) {
     const int row = (int)row0 + lane;
     bool empty = false;
-    if (row < a.M) empty = __ldg(a.rowptr + row) == __ldg(a.rowptr + row + 1);
+    if (row < a.M) {
+      const int deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
+      empty = deg == 0;
+      if (a.hub_flag && deg > a.hub_limit) *a.hub_flag = 1;   // this matrix is not for the row-parallel kernel
+    }
     unsigned m = __ballot_sync(0xffffffffu, empty);
     while (m) {
       const int rr = (int)row0 + (__ffs(m) - 1);
@@ -293,15 +319,17 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
   }
   // ---- part 2: the partials of the SpMM grid must be complete and visible ----
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  const SegLayout sl = seg_layout(a);
+  if (a.nnz_dev && t == 0 && a.nnz_report) *a.nnz_report = sl.nnz;   // the next call's hint (mapped host memory)
   const int nq = a.N / FV;                      // column groups per row
-  const int64_t n_fold = (int64_t)a.num_chunks * nq;
+  const int64_t n_fold = (int64_t)sl.num_chunks * nq;
   if (t < n_fold) {
     const int g = (int)(t / nq);
     const int c = (int)(t % nq) * FV;
     const int r = a.tail_row[g];
     if (r >= 0) {
       const int start = __ldg(a.rowptr + r), end = __ldg(a.rowptr + r + 1);
-      const int g_last = (end - 1) / a.chunk;
+      const int g_last = (end - 1) / sl.chunk;
       float acc[FV];
       int arg[FV];
       ld_vec<FV>(acc, a.part_val + ((size_t)g * 2 + 1) * a.N + c);

@@ -25,6 +25,7 @@ SIGNATURES = {
     "dgs_sm_count": (_i32, []),
     "dgs_spmm_workspace_bytes": (_sz, [_i32, _i64, _i32]),
     "dgs_spmm_csr": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _sz, _vp]),
+    "dgs_spmm_last_path": (_i32, []),
     "dgs_spmm_csr_k": (_i32, [_i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _sz, _vp]),
     "dgs_spmm_csr_multi": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _sz, _vp]),
     "dgs_spmm_csr_mcast": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _sz, _vp]),

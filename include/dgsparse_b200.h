@@ -40,6 +40,10 @@ size_t dgs_spmm_workspace_bytes(int N, int64_t nnz, int with_arg);
 int dgs_spmm_csr(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
                  int64_t ldb, float *C, int64_t ldc, int *E, int64_t lde, int reduce, int compute, void *workspace,
                  size_t workspace_bytes, void *stream);
+/* Which kernel family the calling thread's last SpMM launched: 0 = row-segment kernel + fix-up (two launches, any matrix),
+ * 1 = row-parallel single launch (latency regime, matrices the library has seen to have short rows only). */
+int dgs_spmm_last_path(void);
+
 /* The same with K = rows of B (columns of A) stated.  K only sizes the column panels (csrc/spmm.cu pick_panel): when a
  * 64-column panel of B, K x 256 B, would not stay L2-resident the feature axis is processed in narrower panels, one after
  * the other.  dgs_spmm_csr takes K = M (square adjacency). */

@@ -312,3 +312,100 @@ def test_products_like_full_size(K, oracle, graphs):
         again = getattr(G, name)(rp, cc, val.reshape(-1, 1), B) if has_val else getattr(G, name)(rp, cc, B)
         assert torch.equal(out, again), name
         del out, again
+
+
+def test_legacy_spmm_cuda_without_host_sync_survives_in_place_rewrites(oracle, graphs):
+    """spmm_cuda(m, k, rowptr, ...) has no nnz argument.  Ours reads rowptr[m] with a blocking copy only the first time it
+    sees a (rowptr, m) pair; afterwards the grid is sized from a hint and the kernels take the true nnz from the device.
+    Rewrite the CSR IN PLACE under the same pointers — more nonzeros, fewer, back — and require the right answer on every
+    call, including the first one after each rewrite (stale hint: longer segments / idle groups, never a wrong result)."""
+    import dgsparse._lib as L
+    M, Kc, N = 3000, 2500, 32
+    mats = [graphs.random_csr(M, Kc, n, s, empty_frac=0.2, hub=h) for n, s, h in ((40000, 1, 1), (140000, 2, 2), (9000, 3, 0), (400, 4, 0))]
+    cap = max(c.size for _, c in mats)
+    rp = torch.zeros(M + 1, dtype=torch.int32, device="cuda")
+    cc = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    vv = torch.zeros(cap, dtype=torch.float32, device="cuda")
+    B = graphs.uniform(Kc * N, 9, -1, 1).reshape(Kc, N)
+    dB = dev(B)
+    out = torch.empty(M, N, device="cuda")
+    for which in (0, 0, 1, 1, 1, 2, 2, 3, 3, 0, 1):
+        rowptr, col = mats[which]
+        val = graphs.uniform(col.size, 10 + which, 0.5, 1.5)
+        rp.copy_(torch.from_numpy(rowptr)); cc[:col.size].copy_(torch.from_numpy(col)); vv[:col.size].copy_(torch.from_numpy(val))
+        out.fill_(float("nan"))
+        torch.cuda.synchronize()
+        L.lib.spmm_cuda(M, N, rp.data_ptr(), cc.data_ptr(), vv.data_ptr(), dB.data_ptr(), out.data_ptr())
+        torch.cuda.synchronize()
+        assert_close_f32(out.cpu().numpy(), oracle.spmm(rowptr, col, val, B), oracle.spmm_f64(rowptr, col, val, B),
+                         what=f"in-place matrix {which}", absref=spmm_absref(oracle, rowptr, col, val, B))
+
+
+@pytest.mark.parametrize("N", [4, 16, 32, 64, 100, 128, 256])
+def test_row_parallel_kernel_forced(K, oracle, graphs, monkeypatch, N):
+    """spmm_rowpar_kernel (single launch, a lane group per row) forced on with DGS_SPMM_ROWPAR=1: every reduce, with and
+    without edge values, empty rows, and rows far longer than it would ever be chosen for (hub = 2) — it must be correct
+    for ANY matrix, its selection is only a performance decision."""
+    import dgsparse._lib as L
+    monkeypatch.setenv("DGS_SPMM_ROWPAR", "1")
+    M, Kc = 3000, 2500
+    rowptr, col = graphs.random_csr(M, Kc, 60000, 500 + N, empty_frac=0.3, hub=2)
+    val = graphs.uniform(col.size, 1, 0.5, 1.5)
+    B = graphs.uniform(Kc * N, 2, -1.0, 1.0).reshape(Kc, N)
+    d = [dev(rowptr), dev(col), dev(val), dev(B)]
+    for reduce in ("sum", "mean", "max", "min"):
+        for v, hv in ((d[2], val), (None, None)):
+            wa = reduce in ("max", "min")
+            got = K.spmm(d[0], d[1], v, d[3], RED[reduce], COMP["mul"], with_arg=wa)
+            assert L.lib.dgs_spmm_last_path() == 1
+            if wa:
+                ref, Eref = oracle.spmm(rowptr, col, hv, B, reduce, "mul", with_arg=True)
+                assert np.array_equal(got[0].cpu().numpy(), ref) and np.array_equal(got[1].cpu().numpy(), Eref)
+            else:
+                assert_close_f32(got.cpu().numpy(), oracle.spmm(rowptr, col, hv, B, reduce), oracle.spmm_f64(rowptr, col, hv, B, reduce),
+                                 what=f"rowpar N={N} {reduce}", absref=spmm_absref(oracle, rowptr, col, hv, B, reduce))
+
+
+def test_row_parallel_selected_by_graph_note_and_healed(K, oracle, graphs):
+    """The library learns from its own fix-up scan that a matrix has short rows only (p2p-Gnutella31: longest row 78) and
+    switches later calls to the single-launch kernel; a matrix with a long row never switches; and a CSR rewritten IN PLACE
+    with a long row under the same pointer sends the calls back to the segment path after the row-parallel kernel met it."""
+    import dgsparse._lib as L
+    rowptr, col, (M, Kc) = graphs.load_fixture("p2p-Gnutella31")
+    N = 32
+    val = graphs.uniform(col.size, 1)
+    B = graphs.uniform(Kc * N, 2).reshape(Kc, N)
+    ref = oracle.spmm(rowptr, col, val, B)
+    rp, cc, vv, dB = dev(rowptr), dev(col), dev(val), dev(B)
+    paths = []
+    for _ in range(6):
+        out = K.spmm(rp, cc, vv, dB)
+        paths.append(L.lib.dgs_spmm_last_path())
+        torch.cuda.synchronize()
+        assert_close_f32(out.cpu().numpy(), ref, what="gnutella")
+    assert paths[0] == 0 and paths[-1] == 1, paths
+    # a hub matrix stays on the segment path
+    hr, hc = graphs.random_csr(4000, 4000, 100000, 3, hub=1)
+    hrp, hcc, hB = dev(hr), dev(hc), dev(graphs.uniform(4000 * N, 4).reshape(4000, N))
+    for _ in range(4):
+        K.spmm(hrp, hcc, None, hB)
+        torch.cuda.synchronize()
+        assert L.lib.dgs_spmm_last_path() == 0
+    # rewrite the Gnutella CSR in place: one row of 5000 nonzeros (same rowptr pointer and M)
+    r2 = rowptr.copy()
+    big = int(np.argmax(np.diff(rowptr)))
+    grow = 5000 - int(rowptr[big + 1] - rowptr[big])
+    r2[big + 1:] += grow
+    c2 = np.concatenate([col[:rowptr[big]], np.sort(np.random.default_rng(0).choice(Kc, 5000, replace=False)).astype(np.int32),
+                         col[rowptr[big + 1]:]])
+    v2 = graphs.uniform(c2.size, 5)
+    cc2, vv2 = dev(c2), dev(v2)
+    rp.copy_(torch.from_numpy(r2))
+    ref2 = oracle.spmm(r2, c2, v2, B)
+    paths = []
+    for _ in range(4):
+        out = K.spmm(rp, cc2, vv2, dB)
+        paths.append(L.lib.dgs_spmm_last_path())
+        torch.cuda.synchronize()
+        assert_close_f32(out.cpu().numpy(), ref2, oracle.spmm_f64(r2, c2, v2, B), what="rewritten", absref=oracle.spmm_f64(r2, c2, v2, B))
+    assert paths[0] == 1 and paths[-1] == 0, paths
