@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs 3 / 4 block appended to the default N=1 run")
+    ap.add_argument("--no-legs", action="store_true", help="N>1: skip the compute-only / comm-only / strong-scaling legs")
     return ap.parse_args()
 
 
@@ -60,12 +62,19 @@ def peaks():
 
 
 def ncu_traffic(workload):
-    """Per-launch DRAM traffic of the dominant kernel from the committed ncu capture (profiles/traffic.json)."""
+    """Per-launch DRAM traffic of the dominant kernel from the committed ncu capture (profiles/traffic.json) — only when
+    that capture was taken on the kernel sources this run uses (tools/csrc_hash.py); a capture older than the code reads
+    as null instead of going stale silently.  -> (bytes or None, note)."""
+    from tools import csrc_hash
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p))[workload]["traffic_bytes"]
+        ent = json.load(open(p))[workload]
     except Exception:
-        return None
+        return None, "no ncu capture recorded for this workload"
+    now = csrc_hash.family_hash(ent.get("family", "spmm"))
+    if ent.get("csrc_sha") != now:
+        return None, f"capture {ent.get('source')} predates the current kernel sources ({ent.get('csrc_sha')} != {now})"
+    return ent["traffic_bytes"], f"{ent.get('source')} ({ent.get('kernel')})"
 
 
 def algorithmic_bytes_spmm(M, nnz, N, k_touched, has_value, with_arg=False):
@@ -246,6 +255,104 @@ def reference_cuda_run(wl, M, N, nnz, rp, cc, vv, B, D1, D2, our_step, steps, wa
             "note": "device-resident, default stream, same buffers and step count as `value`"}
 
 
+def sampled_rows_ok(rowptr, rp, cc, vv, B, C, reduce_name, n_rows=64):
+    """fp64 recompute of a sample of rows (the 8 longest included) on the device: parity evidence inside the bench run.
+    sum / mean: |C - ref| <= 1e-5 |ref| + 1e-6 * sum|terms|;  max: exact (fp32 products)."""
+    import torch
+    M = rowptr.size - 1
+    rows = np.unique(np.concatenate([np.linspace(0, M - 1, n_rows).astype(np.int64), np.argsort(np.diff(rowptr))[-8:]]))
+    for r in rows:
+        s, e = int(rowptr[r]), int(rowptr[r + 1])
+        if e == s:
+            if not bool((C[r] == 0).all()):
+                return False
+            continue
+        t32 = B[cc[s:e].long()]
+        if vv is not None:
+            t32 = t32 * vv[s:e][:, None]
+        if reduce_name == "max":
+            if not torch.equal(C[r], t32.max(0).values):
+                return False
+            continue
+        t = t32.double()
+        want, mag = t.sum(0), t.abs().sum(0)
+        if reduce_name == "mean":
+            want, mag = want / (e - s), mag / (e - s)
+        if not bool(((C[r].double() - want).abs() <= 1e-5 * want.abs() + 1e-6 * mag).all()):
+            return False
+    return True
+
+
+def secondary_run(name, args, dev, hbm_peak):
+    """BASELINE configs 3 and 4 inside the driver-run record: products-like feat 128 (gspmm u_mul_e_max) and arxiv-like
+    K 256 (SDDMM), each device-timed like the headline (CUDA events, warm-up, inputs larger than the L2), with the
+    per-launch kernel time, the roofline fraction, a parity check and the reference's own CUDA on the same buffers."""
+    import torch
+    import dgsparse._kernels as K
+    import dgsparse._lib as L
+    wl = make_workload(name, 1.0)
+    rowptr, col, N = wl["rowptr"], wl["col"], wl["N"]
+    M, nnz = rowptr.size - 1, int(col.size)
+    k_touched = int(np.unique(col).size)
+    rp, cc = torch.from_numpy(rowptr).to(dev), torch.from_numpy(col).to(dev)
+    gen = torch.Generator(dev).manual_seed(4321)
+    steps, warm = 10, 3
+    if wl["op"] == "sddmm_csr":
+        vv = None
+        D1, D2 = torch.rand(M, N, device=dev, generator=gen), torch.rand(M, N, device=dev, generator=gen)
+        out = torch.empty(1, nnz, device=dev)
+
+        def step():
+            L.check(L.lib.dgs_sddmm_csr(M, N, nnz, rp.data_ptr(), cc.data_ptr(), D1.data_ptr(), N, D2.data_ptr(), N,
+                                        None, 0, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "sddmm")
+        alg_bytes = 4 * (M + 1) + 4 * nnz + 4 * M * N + 4 * k_touched * N + 4 * nnz
+        main_id, B = 3, None
+    else:
+        vv = torch.rand(nnz, device=dev, generator=gen) + 0.5
+        B = torch.rand(M, N, device=dev, generator=gen)
+        D1 = D2 = None
+        out = torch.empty(M, N, device=dev)
+
+        def step():
+            K.spmm(rp, cc, vv, B, L.MAX, L.MUL, out=out)
+        alg_bytes = algorithmic_bytes_spmm(M, nnz, N, k_touched, True)
+        main_id = 1
+    flop = 2.0 * nnz * N
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    L.lib.dgs_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ids, ms = (ctypes.c_int * 64)(), (ctypes.c_float * 64)()
+    nrec = L.lib.dgs_profile_collect(64, ids, ms)
+    L.lib.dgs_profile_enable(0)
+    kern = [ms[i] for i in range(nrec) if ids[i] == main_id]
+    step_ms = e0.elapsed_time(e1) / steps
+    k_avg = sum(kern) / len(kern) if kern else step_ms
+    if wl["op"] == "sddmm_csr":
+        e = np.unique(np.concatenate([np.linspace(0, nnz - 1, 256).astype(np.int64)]))
+        rows = np.searchsorted(rowptr, e, side="right") - 1
+        want = (D1[torch.from_numpy(rows).to(dev)].double() * D2[cc[torch.from_numpy(e).to(dev)].long()].double()).sum(1)
+        got = out[0][torch.from_numpy(e).to(dev)].double()
+        ok = bool(((got - want).abs() <= 1e-5 * want.abs()).all())     # inputs >= 0: purely relative
+    else:
+        ok = sampled_rows_ok(rowptr, rp, cc, vv, B, out, "max")
+    traffic, tnote = ncu_traffic(name)
+    res = {"workload": f"{wl['op']} on {wl['name']}, M=K={M}, nnz={nnz}, feat={N}, fp32", "steps": steps, "warmup": warm,
+           "ms_per_step": step_ms, "value": flop / (step_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "parity_ok": ok,
+           "roofline": {"bound": "hbm", "achieved": alg_bytes / (k_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (k_avg * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "traffic_source": tnote,
+                        "kernel_ms_avg": k_avg, "algorithmic_bytes_per_launch": alg_bytes}}
+    if not args.no_ref_cuda:
+        res["reference_cuda"] = reference_cuda_run(wl, M, N, nnz, rp, cc, vv, B, D1, D2, step, steps, warm, flop)
+    return res
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -292,6 +399,7 @@ def main():
     k_touched = int(np.unique(col).size) if nnz < 5e8 else M
     val = graphs.uniform(nnz, 1) if wl["has_value"] else None
     hbm_peak, peak_src = peaks()
+    has_value = val is not None
 
     rp, cc = torch.from_numpy(rowptr).to(dev), torch.from_numpy(col).to(dev)
     vv = torch.from_numpy(val).to(dev) if val is not None else None
@@ -410,7 +518,93 @@ def main():
         ref_cuda = reference_cuda_run(wl, M, N, nnz, rp, cc, vv, locals().get("B"), locals().get("D1"),
                                       locals().get("D2"), step, args.steps, max(args.warmup, 3), flop)
 
+    # --- parity inside the bench run (every N): the C this rank now holds against a local single-GPU recompute ---------
+    parity = None
+    if wl["op"] != "sddmm_csr":
+        from dgsparse.distributed import panels_to_row_major
+        red_name = "max" if "max" in wl["op"] else "sum"
+        C_all = sh(B)
+        if sh.mode == "nccl":
+            C_all = panels_to_row_major(C_all)
+        torch.cuda.synchronize()
+        ok, what = True, []
+        if world > 1:
+            # every rank regenerates every rank's B panel (same seeds, same device RNG) and runs the single-GPU kernel on
+            # it: the fused multicast / peer-store exchange must have delivered all N panels bit-identically
+            for r in range(world):
+                Br = torch.rand(M, N, device=dev, generator=torch.Generator(dev).manual_seed(1234 + r))
+                ref_panel = K.spmm(rp, cc, vv, Br, reduce, L.MUL)
+                ok = ok and bool(torch.equal(C_all[:, r * N:(r + 1) * N], ref_panel))
+                del Br, ref_panel
+            what.append(f"all {world} column panels of C[M,{N * world}] on every rank bit-identical to a local single-GPU recompute")
+        ok = ok and sampled_rows_ok(rowptr, rp, cc, vv, B, C_all[:, rank * N:(rank + 1) * N], red_name)
+        what.append("72 sampled rows (8 longest included) of this rank's panel against an fp64 recompute, 1e-5 relative")
+        okt = torch.tensor([1 if ok else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        parity = {"parity_ok": bool(okt.item()), "checked": "; ".join(what)}
+
+    # --- N>1: where the step time goes and a strong-scaling leg (feat 512 in total) ----------
+    legs = None
+    if wl["op"] != "sddmm_csr" and not args.no_legs:
+        def timed(fn, n=5, warm=2):
+            for _ in range(warm):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            barrier()
+            tt = torch.tensor([a.elapsed_time(b) / n], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        legs = {}
+        if world > 1:
+            C_loc = torch.empty(M, N, device=dev)
+            panels = torch.empty(world, M, N, device=dev)
+            flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            legs["compute_only_ms"] = timed(lambda: K.spmm(rp, cc, vv, B, reduce, L.MUL, out=C_loc))
+            legs["comm_only_ms"] = timed(lambda: dist.all_gather_into_tensor(panels, C_loc))
+            legs["barrier_only_ms"] = timed(lambda: sh.barrier(), n=20)
+            legs["nccl_allreduce_1int_ms"] = timed(lambda: dist.all_reduce(flag), n=20)
+            legs["note"] = ("max over ranks; compute_only = the single-GPU kernel + fix-up with local stores, comm_only = one "
+                            "ncclAllGather of the [M, 64] panels (the unfused baseline's exchange), barrier_only = what closes a fused step "
+                            "(dgs_mcast_barrier: one multimem.red + spin, in mcast mode; the one-int NCCL all-reduce it replaced is timed "
+                            "beside it); end to end = ms_per_step")
+            del C_loc, panels
+        if 512 % world == 0:
+            n_s = 512 // world
+            Bs = torch.rand(M, n_s, device=dev, generator=torch.Generator(dev).manual_seed(99 + rank))
+            shs = ColumnShardedSpMM(rp, cc, vv, n_s, reduce=reduce, compute=L.MUL, mode=args.mode)
+            t_s = timed(lambda: shs(Bs), n=5 if world > 1 else 3)
+            legs["strong_leg"] = {"feat_total": 512, "feat_per_gpu": n_s, "ms_per_step": t_s, "exchange": shs.mode,
+                                  "value": 2.0 * nnz * 512 / (t_s * 1e-3) / 1e9, "unit": "GFLOP/s",
+                                  "note": "SURVEY 8d config 5 as STRONG scaling: total feature width fixed at 512"}
+            shs.close()
+            del shs, Bs
+        torch.cuda.empty_cache()
+
+    # --- configs 3 and 4 in the same record (N=1 default run only) ------------------------------------------------------
+    secondary = None
+    if world == 1 and args.workload == "reddit64" and args.scale == 1.0 and not args.no_secondary:
+        keep = (M, nnz, N)
+        sh.close()
+        rp = cc = vv = B = sh = C_all = None      # release the headline workload's device memory (closures see the cells)
+        torch.cuda.empty_cache()
+        secondary = {}
+        for name in ("products128", "arxiv256"):
+            try:
+                secondary[name] = secondary_run(name, args, dev, hbm_peak)
+            except Exception as ex:
+                secondary[name] = {"error": repr(ex)}
+            torch.cuda.empty_cache()
+        M, nnz, N = keep
+
     if rank == 0:
+        traffic, traffic_note = ncu_traffic(args.workload)
         k_avg = sum(kern_ms) / max(1, len(kern_ms)) if kern_ms else ms_per_step
         achieved = alg_bytes / (k_avg * 1e-3) / 1e9
         line = {
@@ -419,13 +613,14 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl['op']} on {wl['name']}, M=K={M}, nnz={nnz}, feat={N} per GPU "
-                                   f"({N * world} total), fp32, edge values {'present' if vv is not None else 'absent'}",
+                                   f"({N * world} total), fp32, edge values {'present' if has_value else 'absent'}",
                        "parallelism": f"feature-axis column shard x{world}, CSR replicated, exchange={mode}",
                        "l2": "no flush: inputs per step (%.0f MB) exceed the 126 MB L2" % (alg_bytes / 1e6)},
             "achieved_hbm_gbs": alg_bytes * (world) / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak,
-                         "traffic": ncu_traffic(args.workload) if args.scale == 1.0 else None, "peak_source": peak_src,
+                         "traffic": traffic if args.scale == 1.0 else None, "traffic_source": traffic_note,
+                         "peak_source": peak_src,
                          "kernel": "spmm_rowseg_kernel" if main_id == 1 else "sddmm_ring_kernel",
                          "kernel_ms_avg": k_avg, "fixup_ms_avg": (sum(fix_ms) / len(fix_ms)) if fix_ms else None,
                          "algorithmic_bytes_per_launch": alg_bytes,
@@ -438,6 +633,12 @@ def main():
             "clocks": clocks,
         }
         line.update(extra)
+        if parity is not None:
+            line.update(parity)
+        if legs:
+            line["legs"] = legs
+        if secondary is not None:
+            line["secondary"] = secondary
         if e2e is not None:
             line["e2e"] = e2e
         if ref_cuda is not None:

@@ -10,6 +10,7 @@
 #include "../../include/dgsparse_b200.h"
 #include "common.cuh"
 #include "spmm.h"
+#include "options.h"
 #include "spconv.h"
 #include "kmap.h"
 
@@ -130,6 +131,24 @@ __global__ void __launch_bounds__(256) coo_to_rowptr_kernel(const int *__restric
   rowptr[r] = lo;
 }
 
+// ---- completion barrier of the fused multicast epilogue ---------------------------------------------------------
+// One thread per rank: add 1 to EVERY rank's arrival counter with a single multimem.red through the NVSwitch (release:
+// ordered behind this rank's multicast stores of the step, which the stream placed before this kernel), then spin on the
+// LOCAL copy until all `world` arrivals of this epoch are in (acquire).  Replaces a one-int ncclAllReduce (~40 us at 8
+// GPUs) as the end-of-step barrier.  The counter only grows (epoch * world), compared wrap-safe.  A rank that never
+// arrives would hang the others: the spin is bounded (~2 s) and then traps, loudly.
+__global__ void mcast_barrier_kernel(unsigned *mc_ctr, const unsigned *local_ctr, unsigned target) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_ctr), "r"(1u) : "memory");
+  const long long t0 = clock64();
+  unsigned v;
+  while (true) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local_ctr) : "memory");
+    if ((int)(v - target) >= 0) break;
+    if (clock64() - t0 > 4000000000LL) { asm volatile("trap;"); }
+  }
+}
+
 // ---- edge softmax --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) edge_softmax_kernel(int M, int head, const int *__restrict__ rowptr,
                                                            const float *__restrict__ v, float *__restrict__ out) {
@@ -158,6 +177,7 @@ int dgs_cuda_version(void) { return CUDA_VERSION; }
 const char *dgs_last_error(void) { return g_err; }
 int dgs_sm_count(void) { return dgs::device_sm_count(); }
 int dgs_spmm_last_path(void) { return dgs::spmm_last_path(); }
+int dgs_set_option(const char *name, int value) { return dgs::set_option(name, value); }
 
 size_t dgs_spmm_workspace_bytes(int N, int64_t nnz, int with_arg) {
   return dgs::spmm_workspace_bytes(N, nnz, with_arg != 0);
@@ -214,6 +234,12 @@ int dgs_spmm_csr_mask(int M, int N, int64_t nnz, const int *ptr, const int *idx,
   p.n_dst = 1; p.dst[0] = out; p.ldc = ldo; p.reduce = dgs::R_SUM; p.compute = dgs::C_MASK;
   p.mask = E; p.ldm = lde;
   return ok_or(dgs::spmm_csr(p, workspace, workspace_bytes, (cudaStream_t)stream), "dgs_spmm_csr_mask");
+}
+
+int dgs_mcast_barrier(void *mc_counter, const void *local_counter, unsigned target, void *stream) {
+  if (mc_counter == nullptr || local_counter == nullptr) return fail(cudaErrorInvalidValue, "dgs_mcast_barrier(pointers)");
+  mcast_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned *)mc_counter, (const unsigned *)local_counter, target);
+  return ok_or(cudaGetLastError(), "dgs_mcast_barrier");
 }
 
 int dgs_sddmm_csr(int M, int K, int64_t nnz, const int *rowptr, const int *col, const float *D1, int64_t ld1,

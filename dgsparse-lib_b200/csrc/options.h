@@ -1,0 +1,16 @@
+// options.h — experiment / test knobs of the library.  Read ONCE from the environment (a getenv per knob per call was a
+// measurable part of a 15 us call), overridable at run time with dgs_set_option(name, value) (tests, tools).
+//   name             environment variable      meaning (unset = -1 = the library decides)
+//   spmm_rowpar      DGS_SPMM_ROWPAR           0 never / 1 always take the row-parallel single-launch SpMM
+//   spmm_panel       DGS_SPMM_PANEL            32: 32-column panels (8-lane geometry) on matrices wider than 32
+//   spmm_no_pdl      DGS_SPMM_NO_PDL           1: fix-up grid not launched as a programmatic dependent
+//   spmm_segs        DGS_SPMM_SEGS             segments per resident lane group
+//   sddmm_no_ring    DGS_SDDMM_NO_RING         1: register-staged SDDMM kernel for every K
+//   sddmm_stages     DGS_SDDMM_STAGES          2 | 3 ring stages
+#pragma once
+
+namespace dgs {
+enum Option { OPT_SPMM_ROWPAR = 0, OPT_SPMM_PANEL, OPT_SPMM_NO_PDL, OPT_SPMM_SEGS, OPT_SDDMM_NO_RING, OPT_SDDMM_STAGES, OPT_COUNT };
+int option(Option o);                          // -1 when unset
+int set_option(const char *name, int value);   // value < 0 clears the override (back to the environment); 0 ok, -1 unknown name
+}  // namespace dgs

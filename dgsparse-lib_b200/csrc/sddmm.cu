@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "spmm.h"
+#include "options.h"
 
 namespace dgs {
 
@@ -436,7 +437,10 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
   const bool vec4 = (p.K % 4 == 0) && (p.ld1 % 4 == 0) && (p.ld2 % 4 == 0) && al16(p.D1) && al16(p.D2) &&
                     (!mask || al16(p.E));
   // rows of 256 B .. 4 KB made of aligned 16-byte chunks: shared-memory ring kernel
-  if (vec4 && !mask && p.K >= 64 && p.K <= 1024 && !getenv("DGS_SDDMM_NO_RING")) {
+  // latency regime (< 1 M edges) at K = 64: one 16-lane pass of the register kernel beats the ring's set-up
+  // (ca-CondMat 19.1 vs 26.8 us, p2p-Gnutella31 14.7 vs 16.7 us; at K >= 128 the ring is level or ahead)
+  const bool small_k64 = p.K == 64 && p.nnz < (1 << 20);
+  if (vec4 && !mask && p.K >= 64 && p.K <= 1024 && !small_k64 && option(OPT_SDDMM_NO_RING) != 1) {
     SddmmRingArgs g;
     SddmmArgs &a = g.a;
     a.M = p.M; a.K = p.K; a.nnz = (int)p.nnz;
@@ -446,7 +450,7 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
     g.slot_bytes = ((uint32_t)p.K * 4u + 127u) & ~127u;
     // ring geometry: 4 edges per batch, STAGES batches per warp ring; as many warps as ~200 KB of ring allow
     int STAGES = 2;
-    if (const char *e = getenv("DGS_SDDMM_STAGES")) STAGES = atoi(e) == 3 ? 3 : 2;
+    if (option(OPT_SDDMM_STAGES) == 3) STAGES = 3;
     g.warp_bytes = (uint32_t)STAGES * 2u * kRgNB * g.slot_bytes + (uint32_t)kRgMetaBytes;
     g.warp_bytes = (g.warp_bytes + 127u) & ~127u;
     int wpc = (int)((200u * 1024u) / g.warp_bytes);

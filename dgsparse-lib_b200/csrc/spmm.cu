@@ -6,6 +6,7 @@
 #include <vector>
 #include <mutex>
 #include "spmm.h"
+#include "options.h"
 #include "spmm_rowseg.cuh"
 #include "spmm_rowpar.cuh"
 
@@ -127,9 +128,9 @@ int g_note_clock = 0;
 
 thread_local int g_last_path = 0;   // 0 = row-segment kernel + fix-up, 1 = row-parallel single launch
 
-int rowpar_mode() {   // DGS_SPMM_ROWPAR: 0 = never, 1 = always (tests), unset = by graph note
-  const char *e = getenv("DGS_SPMM_ROWPAR");
-  return e ? (atoi(e) ? 1 : 0) : -1;
+int rowpar_mode() {   // option spmm_rowpar: 0 = never, 1 = always (tests), unset (-1) = by graph note
+  const int v = option(OPT_SPMM_ROWPAR);
+  return v < 0 ? -1 : (v ? 1 : 0);
 }
 
 // -> index of the note (creating it on first sight), or -1
@@ -210,13 +211,10 @@ int device_l2_bytes() {
 // lines; a miss costs ~126 B of DRAM whatever the request size; (2) even fully resident (reddit-like N=128, 15 MB of
 // slices) the gather is bound by REQUESTS, not bytes: 141 / 171 / 183 G requests/s at 128 / 64 / 32 B per request, i.e.
 // 18 / 10.9 / 5.9 TB/s — a repacked contiguous 8-column panel would top out at 1.98 G requests / 183 G/s = 10.8 ms.
-// Only >= 128 B per request runs at full L2 rate.  DGS_SPMM_PANEL=32 keeps the 8-lane geometry reachable for experiments.
+// Only >= 128 B per request runs at full L2 rate.  Option spmm_panel = 32 keeps the 8-lane geometry reachable for experiments.
 static int pick_panel(int N, int64_t K, bool narrow_ok) {
   (void)N; (void)K; (void)narrow_ok;
-  if (const char *e = getenv("DGS_SPMM_PANEL")) {
-    if (atoi(e) == 32) return 32;
-  }
-  return 64;
+  return option(OPT_SPMM_PANEL) == 32 ? 32 : 64;
 }
 
 // Lane-group geometry for feature width N and panel width W.  vec4 needs 16-byte aligned rows everywhere.
@@ -241,19 +239,17 @@ static constexpr size_t kWorkspaceCap = 192u << 20;
 // cut by a segment boundary (those are finished by the fix-up kernel, which on N GPUs is an NVLink-ingress burst).
 // Measured on B200 (DGS_SPMM_SEGS sweep): the main kernel does not care (reddit@64 1.573 / 1.568 / 1.567 / 1.570 / 1.575 ms
 // for 8 / 4 / 3 / 2 / 1, products@128 8.95 / 8.93 / 8.95 ms for 8 / 4 / 3) while the fix-up shrinks from 0.018 to 0.013 ms.
-static int segs_per_group() {
-  static int v = 0;
-  if (v == 0) {
-    const char *e = getenv("DGS_SPMM_SEGS");
-    v = e ? atoi(e) : 4;
-    if (v < 1 || v > 64) v = 4;
-  }
-  return v;
+// remote = the epilogue also stores to other GPUs (peer pointers or the NVLS multicast address): one segment per resident
+// group, so that as few rows as possible are cut and finished by the fix-up grid's burst over NVLink.
+static int segs_per_group(bool remote) {
+  const int v = option(OPT_SPMM_SEGS);
+  if (v >= 1 && v <= 64) return v;
+  return remote ? 1 : 4;
 }
 
-static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
+static int pick_chunk(int N, int64_t nnz, bool with_arg, int G, bool remote) {
   const int64_t resident_groups = (int64_t)device_sm_count() * 3 * (kSpmmThreads / G);
-  const int spg = segs_per_group();
+  const int spg = segs_per_group(remote);
   int64_t chunk = (nnz + resident_groups * spg - 1) / (resident_groups * spg);
   // Small matrices (latency regime): one 32-nnz batch per segment spreads them over more SMs; with two or more column
   // panels (N > 64) the extra cut rows cost more than that buys.  p2p-Gnutella31 / ca-CondMat, us per call, min 32 | 64 | 128:
@@ -276,10 +272,10 @@ static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static void geometry_for(int N, int64_t nnz, bool with_arg, bool can_vec4, int W, int *vec, int *G, bool *narrow,
+static void geometry_for(int N, int64_t nnz, bool with_arg, bool can_vec4, int W, bool remote, int *vec, int *G, bool *narrow,
                          int *chunk, int *num_chunks) {
   pick_geometry(N, W, can_vec4, vec, G, narrow);
-  *chunk = pick_chunk(N, nnz, with_arg, *G);
+  *chunk = pick_chunk(N, nnz, with_arg, *G, remote);
   *num_chunks = (int)((nnz + *chunk - 1) / *chunk);
 }
 
@@ -291,7 +287,7 @@ size_t spmm_workspace_bytes(int N, int64_t nnz, bool with_arg) {
     static const int widths[3] = {64, 32, 64};
     int vec, G, chunk, nc;
     bool narrow;
-    geometry_for(N, nnz, with_arg, pass < 2, widths[pass], &vec, &G, &narrow, &chunk, &nc);
+    geometry_for(N, nnz, with_arg, pass < 2, widths[pass], false, &vec, &G, &narrow, &chunk, &nc);   // local: the most segments
     size_t b = align_up((size_t)nc * 4, 256) + align_up((size_t)nc * 2 * N * 4, 256) * (with_arg ? 2 : 1);
     if (b > need) need = b;
   }
@@ -357,7 +353,7 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   g_last_path = 0;
   if (p.nnz > 0) {
     const int W = pick_panel(p.N, p.K > 0 ? p.K : p.M, false);
-    geometry_for(p.N, p.nnz, with_arg, can_vec4, W, &vec, &G, &narrow, &a.chunk, &a.num_chunks);
+    geometry_for(p.N, p.nnz, with_arg, can_vec4, W, p.n_dst > 1 || p.mcast != 0, &vec, &G, &narrow, &a.chunk, &a.num_chunks);
     const size_t tail_b = align_up((size_t)a.num_chunks * 4, 256);
     const size_t part_b = align_up((size_t)a.num_chunks * 2 * p.N * 4, 256);
     const size_t need = tail_b + part_b * (with_arg ? 2 : 1);
@@ -395,7 +391,7 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   const int64_t threads = fold_threads > empty_threads ? fold_threads : empty_threads;
   const int blocks = (int)((threads + 255) / 256);
   // dependent launch only right behind the SpMM grid, and not while the bench brackets the two launches with events
-  const bool pdl = p.nnz > 0 && !profile_is_on() && !getenv("DGS_SPMM_NO_PDL");
+  const bool pdl = p.nnz > 0 && !profile_is_on() && option(OPT_SPMM_NO_PDL) != 1;
   cudaError_t fe;
   {
     ProfileScope prof(2, stream);

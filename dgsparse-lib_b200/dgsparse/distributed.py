@@ -12,7 +12,9 @@ output panel is then made available on every rank, in one of two ways:
   mode="mcast" (tried first when the ranks share an NVSwitch): the same fused epilogue, but C lives in torch symmetric
                memory and every finished row segment is stored ONCE to the NVLS multicast address
                (multimem.st, dgs_spmm_csr_mcast): the switch replicates it into every rank's C, so a rank sends
-               M*n_local*4 bytes per step instead of (world-1) times that.
+               M*n_local*4 bytes per step instead of (world-1) times that.  The end-of-step barrier is ours too: one
+               multimem.red on an arrival counter in symmetric memory + a spin on the local copy (dgs_mcast_barrier),
+               instead of a one-int NCCL all-reduce.
   mode="nccl"  the baseline: local SpMM, then one ncclAllGather of the [M, n_local] panel into a
                panel-major [world, M, n_local] buffer (panels_to_row_major() permutes when needed).
 
@@ -28,6 +30,7 @@ One process per GPU (torchrun); torch.distributed is used for the rendezvous, th
 and the barrier only.
 """
 import ctypes
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -111,6 +114,17 @@ class ColumnShardedSpMM:
             raise RuntimeError("symmetric memory has no multicast mapping on this box")
         self.C, self._symm = C, hdl
         self._mc_dst = mc + self.lo * 4
+        # arrival counter of the end-of-step barrier (dgs_mcast_barrier): its own symmetric allocation, zeroed everywhere first
+        self._bar = symm.empty((64,), dtype=torch.int32, device=dev)
+        self._bar.zero_()
+        bh = symm.rendezvous(self._bar, group)
+        self._bar_mc = int(getattr(bh, "multicast_ptr", 0) or 0)
+        self._bar_hdl = bh
+        self._epoch = 0
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+        if self._bar_mc == 0 or os.environ.get("DGS_MCAST_BARRIER") == "nccl":
+            self._bar_mc = 0
 
     def _map_peers(self):
         L = self._lib
@@ -152,7 +166,7 @@ class ColumnShardedSpMM:
                                            ptr(B_local), B_local.stride(0), self._mc_dst + buf * self.M * self.n_total * 4,
                                            self.n_total, self.reduce,
                                            self.compute, ptr(self.ws), self.ws.numel(), stream), "dgs_spmm_csr_mcast")
-            dist.all_reduce(self._flag, group=self.group)   # completion barrier: every rank's multicast stores have landed
+            self.barrier(stream)                            # completion barrier: every rank's multicast stores have landed
             return self.C[buf]
         if self.mode == "local":
             dst = (ctypes.c_void_p * 1)(self.C.data_ptr())
@@ -164,6 +178,20 @@ class ColumnShardedSpMM:
         if self.world > 1:
             dist.all_reduce(self._flag, group=self.group)   # completion barrier: all peers' stores have landed
         return self.C[buf]
+
+    def barrier(self, stream=None):
+        """The end-of-step barrier alone (stream-ordered): dgs_mcast_barrier in mcast mode, else a one-int NCCL all-reduce."""
+        if self.world == 1:
+            return
+        if self.mode == "mcast" and getattr(self, "_bar_mc", 0):
+            if stream is None:
+                stream = torch.cuda.current_stream(self._bar.device).cuda_stream
+            self._epoch += 1
+            L = self._lib
+            L.check(L.lib.dgs_mcast_barrier(self._bar_mc, self._bar.data_ptr(), (self._epoch * self.world) & 0xffffffff, stream),
+                    "dgs_mcast_barrier")
+        else:
+            dist.all_reduce(self._flag, group=self.group)
 
     def close(self):
         for p in self._opened:

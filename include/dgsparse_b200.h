@@ -40,6 +40,10 @@ size_t dgs_spmm_workspace_bytes(int N, int64_t nnz, int with_arg);
 int dgs_spmm_csr(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
                  int64_t ldb, float *C, int64_t ldc, int *E, int64_t lde, int reduce, int compute, void *workspace,
                  size_t workspace_bytes, void *stream);
+/* Experiment / test knobs (csrc/options.h lists them; each is also read once from the environment, DGS_<NAME>):
+ * dgs_set_option("spmm_rowpar", 1) etc.; value < 0 clears the override.  Returns 0, or -1 for an unknown name. */
+int dgs_set_option(const char *name, int value);
+
 /* Which kernel family the calling thread's last SpMM launched: 0 = row-segment kernel + fix-up (two launches, any matrix),
  * 1 = row-parallel single launch (latency regime, matrices the library has seen to have short rows only). */
 int dgs_spmm_last_path(void);
@@ -61,6 +65,13 @@ int dgs_spmm_csr_multi(int M, int N, int64_t nnz, const int *rowptr, const int *
 int dgs_spmm_csr_mcast(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
                        int64_t ldb, float *mc_dst, int64_t ldc, int reduce, int compute, void *workspace,
                        size_t workspace_bytes, void *stream);
+
+/* End-of-step barrier of the multicast exchange: one multimem.red (release) adds 1 to every rank's copy of a 4-byte arrival
+ * counter in symmetric memory (mc_counter = its multicast address), then the kernel spins (acquire) on this rank's own copy
+ * (local_counter) until it reaches `target` = epoch * world.  Stream-ordered behind the SpMM of the step; when it returns on
+ * a stream, every rank's multicast stores of the step are visible to later work on that stream.  The counter must be zeroed
+ * on all ranks before the first epoch. */
+int dgs_mcast_barrier(void *mc_counter, const void *local_counter, unsigned target, void *stream);
 
 /* Masked SpMM of the max/min backward (grad wrt dense), called on the CSC arrays:
  *   out[j, v] = sum_{p in ptr[j]..ptr[j+1]} [E[idx[p], v] == j] * val[p] * G[idx[p], v]

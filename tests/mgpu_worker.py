@@ -48,6 +48,29 @@ def main():
                 print("MULTICAST UNAVAILABLE:", getattr(op, "_mcast_error", "?"), flush=True)
             dist.barrier()
             op.close()
+    # write-after-read across ranks: a different B every step, a SLOW consumer on rank 0 (it sleeps on the stream
+    # before it reads the step's C) and fast producers elsewhere.  The output is double-buffered and every step ends in a
+    # barrier, so step k+1's remote stores must never land in the buffer rank 0 is still reading for step k.
+    for mode in ("mcast", "peer"):
+        op = ColumnShardedSpMM(rp, cc, vv, n_local, reduce=L.SUM, mode=mode)
+        steps = 6
+        stash = []
+        for k in range(steps):
+            Bk = (Bf + float(k)).contiguous()
+            out = op(Bk[:, rank * n_local:(rank + 1) * n_local].contiguous())
+            if rank == 0:
+                torch.cuda._sleep(30_000_000)                      # ~15 ms: the consumer lags, the other ranks run ahead
+            C = out if op.mode in ("peer", "mcast") else panels_to_row_major(out)
+            stash.append(C.clone())
+        torch.cuda.synchronize()
+        ok = all(torch.equal(stash[k], K.spmm(rp, cc, vv, (Bf + float(k)).contiguous())) for k in range(steps))
+        flag = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"slow-consumer stress mode={op.mode} every step identical={bool(flag.item())}", flush=True)
+        assert flag.item() == 1, mode
+        dist.barrier()
+        op.close()
     # host-resident operands: sliced upload + NVLink all-gather of the CSR, own panel back to the host
     from dgsparse.distributed import HostColumnShardedSpMM
     hp = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()

@@ -24,6 +24,20 @@ def K():
     return k
 
 
+@pytest.fixture
+def knob():
+    """dgs_set_option(name, value) for the duration of one test (include/dgsparse_b200.h), cleared afterwards."""
+    import dgsparse._lib as L
+    touched = []
+
+    def set_(name, value):
+        assert L.lib.dgs_set_option(name.encode(), int(value)) == 0, name
+        touched.append(name)
+    yield set_
+    for name in touched:
+        L.lib.dgs_set_option(name.encode(), -1)
+
+
 @pytest.mark.parametrize("name", ["p2p-Gnutella31", "ca-CondMat"])
 def test_config1_golden_feat32(K, oracle, graphs, name):
     """BASELINE config 1: example/data CSR, feat=32, against the reference host function's own output."""
@@ -42,7 +56,11 @@ def test_config1_golden_feat32(K, oracle, graphs, name):
     torch.cuda.synchronize()
     L.lib.spmm_cuda(M, 32, *[t.data_ptr() for t in d], o2.data_ptr())
     torch.cuda.synchronize()
-    assert np.array_equal(o2.cpu().numpy(), out)
+    # same arithmetic; bit-identical only when both calls took the same kernel family (the row-parallel kernel sums a row
+    # in one piece, the segment kernel folds rows cut by a segment boundary), which depends on what the library has seen of
+    # these device pointers before
+    assert_close_f32(o2.cpu().numpy()[g["rows"]], g["out_rows"], what=f"{name} spmm_cuda golden rows")
+    assert np.allclose(o2.cpu().numpy(), out, rtol=1e-5, atol=1e-6)
     o3 = torch.empty(M, 32, device="cuda")
     L.lib.spmm_cuda_no_edge_value(M, 32, d[0].data_ptr(), d[1].data_ptr(), None, d[3].data_ptr(), o3.data_ptr())
     torch.cuda.synchronize()
@@ -245,8 +263,8 @@ def test_full_size_properties(K, graphs):
 
 @pytest.mark.parametrize("panel", ["32"])
 @pytest.mark.parametrize("N", [16, 64, 100, 128, 136, 256])
-def test_narrow_panels_same_as_wide(K, oracle, graphs, monkeypatch, panel, N):
-    """Column panels narrower than 64 (DGS_SPMM_PANEL=32: the 8-lane row-segment geometry on matrices wider than its panel;
+def test_narrow_panels_same_as_wide(K, oracle, graphs, knob, panel, N):
+    """Column panels narrower than 64 (option spmm_panel = 32: the 8-lane row-segment geometry on matrices wider than its panel;
     the 8 / 16-column kernels were a measured dead end, csrc/spmm.cu pick_panel).  Every reduce, with and without edge
     values; max / min and their arg index bit-exact, sum / mean within the stated tolerance (segment boundaries, hence the
     places where a long row's partial sums are folded, differ with the group width, so sums are not bit-identical across
@@ -259,7 +277,7 @@ def test_narrow_panels_same_as_wide(K, oracle, graphs, monkeypatch, panel, N):
     for reduce in ("sum", "mean", "max", "min"):
         for v in (d[2], None):
             wa = reduce in ("max", "min")
-            monkeypatch.setenv("DGS_SPMM_PANEL", panel)
+            knob("spmm_panel", panel)
             got = K.spmm(d[0], d[1], v, d[3], RED[reduce], COMP["mul"], with_arg=wa)
             hv = None if v is None else val
             if wa:
@@ -342,12 +360,12 @@ def test_legacy_spmm_cuda_without_host_sync_survives_in_place_rewrites(oracle, g
 
 
 @pytest.mark.parametrize("N", [4, 16, 32, 64, 100, 128, 256])
-def test_row_parallel_kernel_forced(K, oracle, graphs, monkeypatch, N):
-    """spmm_rowpar_kernel (single launch, a lane group per row) forced on with DGS_SPMM_ROWPAR=1: every reduce, with and
+def test_row_parallel_kernel_forced(K, oracle, graphs, knob, N):
+    """spmm_rowpar_kernel (single launch, a lane group per row) forced on with option spmm_rowpar = 1: every reduce, with and
     without edge values, empty rows, and rows far longer than it would ever be chosen for (hub = 2) — it must be correct
     for ANY matrix, its selection is only a performance decision."""
     import dgsparse._lib as L
-    monkeypatch.setenv("DGS_SPMM_ROWPAR", "1")
+    knob("spmm_rowpar", 1)
     M, Kc = 3000, 2500
     rowptr, col = graphs.random_csr(M, Kc, 60000, 500 + N, empty_frac=0.3, hub=2)
     val = graphs.uniform(col.size, 1, 0.5, 1.5)

@@ -71,3 +71,46 @@ void gen_uniform(int64_t n, uint64_t seed, float lo, float hi, float *x) {
     x[i] = lo + (hi - lo) * ((float)u * (1.0f / 16777216.0f));
   }
 }
+
+/* gen_columns_community: the same, with planted community structure — rows [c*S, (c+1)*S) form community c and every column
+ * of a row is drawn from the row's own community with probability p_intra (per mille), else uniformly from [0, K).  At most
+ * S/2 intra-community columns per row (a hub row spills over to the whole graph).  Same degree sequence, sorted distinct columns. */
+void gen_columns_community(int M, int K, const int64_t *rowptr, uint64_t seed, int S, int p_intra, int *col) {
+#pragma omp parallel
+  {
+    size_t words = ((size_t)K + 63) / 64;
+    uint64_t *bits = (uint64_t *)calloc(words, sizeof(uint64_t));
+#pragma omp for schedule(dynamic, 256)
+    for (int r = 0; r < M; r++) {
+      int64_t lo = rowptr[r];
+      int d = (int)(rowptr[r + 1] - lo);
+      if (d <= 0) continue;
+      if (d > K) d = K;
+      uint64_t s = seed * 0xD1342543DE82EF95ull + (uint64_t)r * 0x2545F4914F6CDD1Dull + 1;
+      int *out = col + lo;
+      int c0 = (r / S) * S, cs = (c0 + S <= K) ? S : (K - c0 > 0 ? K - c0 : 0);
+      int got = 0, intra = 0;
+      while (got < d) {
+        uint32_t c;
+        int want_intra = cs > 0 && intra < cs / 2 && (int)((splitmix64(&s) >> 40) % 1000) < p_intra;
+        if (want_intra) c = (uint32_t)c0 + (uint32_t)(((splitmix64(&s) >> 32) * (uint64_t)cs) >> 32);
+        else c = (uint32_t)(((splitmix64(&s) >> 32) * (uint64_t)K) >> 32);
+        uint64_t m = 1ull << (c & 63);
+        if (!(bits[c >> 6] & m)) {
+          bits[c >> 6] |= m;
+          out[got++] = (int)c;
+          if (want_intra) intra++;
+        } else if (d > K / 2 && !want_intra) {
+          /* dense row: walk to the next free column instead of redrawing forever */
+          uint32_t cc = c;
+          do { cc = (cc + 1 == (uint32_t)K) ? 0 : cc + 1; } while (bits[cc >> 6] & (1ull << (cc & 63)));
+          bits[cc >> 6] |= 1ull << (cc & 63);
+          out[got++] = (int)cc;
+        }
+      }
+      qsort(out, (size_t)d, sizeof(int), cmp_int);
+      for (int i = 0; i < d; i++) bits[out[i] >> 6] &= ~(1ull << (out[i] & 63));
+    }
+    free(bits);
+  }
+}

@@ -77,6 +77,33 @@ def from_degrees(deg, K, seed):
     return rowptr.astype(np.int32), col
 
 
+def from_degrees_community(deg, K, seed, comm_size, p_intra):
+    """from_degrees with planted communities: rows [c*comm_size, (c+1)*comm_size) draw a column from their own community
+    with probability p_intra, else uniformly (tools/graphgen.c gen_columns_community)."""
+    deg = np.asarray(deg, np.int64)
+    M = deg.size
+    rowptr = np.zeros(M + 1, np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    assert rowptr[-1] < 2**31
+    col = np.empty(int(rowptr[-1]), np.int32)
+    _l().gen_columns_community(ctypes.c_int(M), ctypes.c_int(K), rowptr.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(seed),
+                               ctypes.c_int(int(comm_size)), ctypes.c_int(int(round(p_intra * 1000))),
+                               col.ctypes.data_as(ctypes.c_void_p))
+    return rowptr.astype(np.int32), col
+
+
+def reddit_like_communities(scale=1.0, comm_size=1024, p_intra=0.85):
+    """The reddit-like workload (same M, nnz, degree law and seed as reddit_like) with LOCALITY: 85 % of a row's columns
+    fall in the row's own community of `comm_size` consecutive nodes — the structure real social / co-purchase graphs have
+    after a community-aware node ordering, which the uniform generator (the worst case for every cache) lacks."""
+    M = max(64, int(round(232965 * scale)))
+    nnz = int(round(114615892 * scale))
+    rng = np.random.Generator(np.random.PCG64(20240001))
+    raw = rng.lognormal(5.4, 1.3, M)
+    deg = _fit_degrees(raw, nnz, 1, min(21657, M), rng)
+    return from_degrees_community(deg, M, 20240001, comm_size, p_intra)
+
+
 def reddit_like(scale=1.0):
     """M=K=232 965, nnz=114 615 892, lognormal(5.4, 1.3) degrees clipped to [1, 21 657] (§8d config 2).
     scale < 1 shrinks M and nnz together (same mean degree) for parity-sized cases."""
