@@ -23,6 +23,7 @@
 // Fixes of the reference: the output is zeroed by the call, every dtype path writes fp32 into the fp32
 // output, `separate_mid` runs the centre offset as identity-mapped tiles of the same kernel instead of a cuBLAS call.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdlib>
 #include "common.cuh"
@@ -57,6 +58,7 @@ struct SpconvArgs {
   int64_t feat_pitch;        // bytes between rows
   int feat_valid_bytes;      // bytes of a row that hold channels (the rest of the last atom is zero-filled)
   int n_stages;              // shared-memory A stages
+  int f16;                   // 16-bit operand format of the kind::f16 path: 0 = bf16, 1 = fp16 (IEEE half)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -93,9 +95,9 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t saddr) {
 }
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (1 << 4), A/B format in [7,10)/[10,13)
-// (2 = tf32, 1 = bf16), both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
-template <int KIND> __device__ __forceinline__ uint32_t umma_idesc(int n) {
-  const uint32_t fmt = KIND == 0 ? 2u : 1u;
+// (kind::tf32: 2 = tf32; kind::f16: 0 = fp16, 1 = bf16), both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
+template <int KIND> __device__ __forceinline__ uint32_t umma_idesc(int n, int f16) {
+  const uint32_t fmt = KIND == 0 ? 2u : (f16 ? 0u : 1u);
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
@@ -137,6 +139,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t *>(&h);
 }
+// two fp32 -> one 32-bit word of 16-bit operands, round to nearest: fp16 (the reference's half kernels,
+// include/cuda/spconv.cuh:1408-1552: 10 mantissa bits) or bf16 (7 bits, fp32 range)
+__device__ __forceinline__ uint32_t pack_16(float lo, float hi, int f16) {
+  if (f16) { __half2 h = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t *>(&h); }
+  return pack_bf16(lo, hi);
+}
 
 template <int KIND> struct Kind;
 template <> struct Kind<0> { static constexpr int kElemBytes = 4, kElemsPerAtom = 32, kUmmaK = 8; };   // tf32
@@ -144,7 +152,7 @@ template <> struct Kind<1> { static constexpr int kElemBytes = 2, kElemsPerAtom 
 
 // One 16-byte shared-memory chunk of a gathered row: channels [ch, ch + 16 / elem bytes) of `row` (zeros when the
 // row is padding or the channels lie beyond c_in).
-template <int KIND> __device__ __forceinline__ uint4 gather_chunk(const float *in, int64_t ld_in, int row, int ch, int c_in) {
+template <int KIND> __device__ __forceinline__ uint4 gather_chunk(const float *in, int64_t ld_in, int row, int ch, int c_in, int f16) {
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
   if (row < 0) return o;
   const float *src = in + (int64_t)row * ld_in + ch;
@@ -157,7 +165,7 @@ template <int KIND> __device__ __forceinline__ uint4 gather_chunk(const float *i
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
     if (ch < c_in) a = __ldg(reinterpret_cast<const float4 *>(src));
     if (ch + 4 < c_in) b = __ldg(reinterpret_cast<const float4 *>(src + 4));
-    o = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+    o = make_uint4(pack_16(a.x, a.y, f16), pack_16(a.z, a.w, f16), pack_16(b.x, b.y, f16), pack_16(b.z, b.w, f16));
   }
   return o;
 }
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(128) spconv_fgms_tc_kernel(const SpconvArgs a)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-  const uint32_t idesc = umma_idesc<KIND>(a.NT);
+  const uint32_t idesc = umma_idesc<KIND>(a.NT, a.f16);
   const int n0 = blockIdx.y * a.NT;
   uint32_t phase = 0;
   int resident_k = -1;
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(128) spconv_fgms_tc_kernel(const SpconvArgs a)
           const int idx = (it0 + u) * 128 + tid;
           const int c = idx & 7, at = (idx >> 3) % ga, r = idx / (8 * ga);
           const int ch = (a0 + at) * KD::kElemsPerAtom + c * (16 / KD::kElemBytes);
-          v[u] = gather_chunk<KIND>(a.in, a.ld_in, s_inrow[r], ch, a.c_in);
+          v[u] = gather_chunk<KIND>(a.in, a.ld_in, s_inrow[r], ch, a.c_in, a.f16);
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) spconv_fgms_pipe_kernel(const
   } else if (warp == 8) {
     // ================= MMA issue =================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc<KIND>(a.NT);
+      const uint32_t idesc = umma_idesc<KIND>(a.NT, a.f16);
       for (int i = 0; i < n_my; i++) {
         const int s = i % S, t = i & 1;
         mbar_wait(&s_full[s], (uint32_t)(i / S) & 1u);
@@ -535,9 +543,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) spconv_fgms_pipe_kernel(const
   if (warp == 8) tmem_dealloc(tmem, (uint32_t)(2 * a.tmem_cols));
 }
 
-// fp32 features -> bf16 rows of k_pad elements (zero padded), once per call, for the pipelined bf16 gather
+// fp32 features -> bf16 / fp16 rows of k_pad elements (zero padded), once per call, for the pipelined 16-bit gather
 __global__ void __launch_bounds__(256) spconv_to_bf16_kernel(const float *__restrict__ in, int64_t ld_in, int rows, int c_in,
-                                                             int k_pad, __nv_bfloat16 *__restrict__ out) {
+                                                             int k_pad, __nv_bfloat16 *__restrict__ out, int f16) {
   const int chunks = k_pad / 8;
   const int64_t total = (int64_t)rows * chunks;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -545,7 +553,7 @@ __global__ void __launch_bounds__(256) spconv_to_bf16_kernel(const float *__rest
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) v[e] = ch + e < c_in ? __ldg(in + (int64_t)r * ld_in + ch + e) : 0.0f;
-    uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    uint4 o = make_uint4(pack_16(v[0], v[1], f16), pack_16(v[2], v[3], f16), pack_16(v[4], v[5], f16), pack_16(v[6], v[7], f16));
     *reinterpret_cast<uint4 *>(out + (int64_t)r * k_pad + ch) = o;
   }
 }
@@ -554,7 +562,7 @@ __global__ void __launch_bounds__(256) spconv_to_bf16_kernel(const float *__rest
 template <int KIND>
 __global__ void __launch_bounds__(256) spconv_prep_weights_kernel(const float *__restrict__ W, uint8_t *__restrict__ Wt, int k_vol,
                                                                   int kdim, int ndim, int k_pad, int n_rows_pad, int64_t sc,
-                                                                  int64_t sn, int64_t sk) {
+                                                                  int64_t sn, int64_t sk, int f16) {
   const int64_t total = (int64_t)k_vol * n_rows_pad * k_pad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % k_pad);
@@ -563,6 +571,7 @@ __global__ void __launch_bounds__(256) spconv_prep_weights_kernel(const float *_
     float v = 0.0f;
     if (c < kdim && n < ndim) v = __ldg(W + (int64_t)k * sk + (int64_t)c * sc + (int64_t)n * sn);
     if (KIND == 0) reinterpret_cast<uint32_t *>(Wt)[i] = to_tf32(v);
+    else if (f16) reinterpret_cast<__half *>(Wt)[i] = __float2half_rn(v);
     else reinterpret_cast<__nv_bfloat16 *>(Wt)[i] = __float2bfloat16_rn(v);
   }
 }
@@ -912,8 +921,9 @@ struct TcGeometry {
 
 TcGeometry tc_geometry(int kdim, int ndim, int precision) {
   TcGeometry g;
-  const int epa = precision == SPCONV_BF16 ? 64 : 32;
-  g.esize = precision == SPCONV_BF16 ? 2 : 4;
+  const bool b16 = precision == SPCONV_BF16 || precision == SPCONV_FP16;
+  const int epa = b16 ? 64 : 32;
+  g.esize = b16 ? 2 : 4;
   g.n_atoms = (kdim + epa - 1) / epa;
   g.k_pad = g.n_atoms * epa;
   const int n16 = round_up(ndim, 16);
@@ -936,13 +946,14 @@ size_t spconv_workspace_bytes(int rows, int k_vol, int c_in, int c_out, int prec
   const TcGeometry f = tc_geometry(c_in, c_out, precision), b = tc_geometry(c_out, c_in, precision);
   const size_t wf = (size_t)k_vol * f.n_rows_pad * f.k_pad * f.esize, wb = (size_t)k_vol * b.n_rows_pad * b.k_pad * b.esize;
   size_t need = (wf > wb ? wf : wb) + 512;
-  if (precision == SPCONV_BF16) need += (size_t)(rows > 0 ? rows : 0) * (f.k_pad > b.k_pad ? f.k_pad : b.k_pad) * 2 + 256;
+  if (precision == SPCONV_BF16 || precision == SPCONV_FP16) need += (size_t)(rows > 0 ? rows : 0) * (f.k_pad > b.k_pad ? f.k_pad : b.k_pad) * 2 + 256;
   return need;
 }
 
 cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (p.k_vol <= 0 || p.kdim <= 0 || p.ndim <= 0) return cudaErrorInvalidValue;
-  if (p.precision != SPCONV_FP32 && p.precision != SPCONV_TF32 && p.precision != SPCONV_BF16) return cudaErrorInvalidValue;
+  if (p.precision != SPCONV_FP32 && p.precision != SPCONV_TF32 && p.precision != SPCONV_BF16 && p.precision != SPCONV_FP16)
+    return cudaErrorInvalidValue;
   if (p.sum_nnz % kTileM != 0) return cudaErrorInvalidValue;   // qkpos must be quantised to 128 (q of the reference)
   cudaError_t e;
   if (!p.accumulate && p.out_rows > 0) {
@@ -956,6 +967,7 @@ cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspac
   a.kpos = p.kpos; a.qkpos = p.qkpos; a.imap = p.imap; a.omap = p.omap;
   a.in = p.in; a.out = p.out; a.ld_in = p.ld_in; a.ld_out = p.ld_out;
   a.k_vol = p.k_vol; a.c_in = p.kdim; a.c_out = p.ndim;
+  a.f16 = p.precision == SPCONV_FP16 ? 1 : 0;
   a.n_map_tiles = (int)(p.sum_nnz / kTileM);
   a.mid_k = (p.k_vol % 2 == 1) ? p.k_vol / 2 : 0;   // src/cuda/spconv_cuda.cu:35
   a.id_rows = p.separate_mid ? p.in_rows : 0;
@@ -982,9 +994,9 @@ cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspac
   const int64_t total = (int64_t)p.k_vol * g.n_rows_pad * g.k_pad;
   const int prep_blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   if (p.precision == SPCONV_TF32)
-    spconv_prep_weights_kernel<0><<<prep_blocks, 256, 0, stream>>>(p.W, Wt, p.k_vol, p.kdim, p.ndim, g.k_pad, g.n_rows_pad, p.w_sc, p.w_sn, p.w_sk);
+    spconv_prep_weights_kernel<0><<<prep_blocks, 256, 0, stream>>>(p.W, Wt, p.k_vol, p.kdim, p.ndim, g.k_pad, g.n_rows_pad, p.w_sc, p.w_sn, p.w_sk, a.f16);
   else
-    spconv_prep_weights_kernel<1><<<prep_blocks, 256, 0, stream>>>(p.W, Wt, p.k_vol, p.kdim, p.ndim, g.k_pad, g.n_rows_pad, p.w_sc, p.w_sn, p.w_sk);
+    spconv_prep_weights_kernel<1><<<prep_blocks, 256, 0, stream>>>(p.W, Wt, p.k_vol, p.kdim, p.ndim, g.k_pad, g.n_rows_pad, p.w_sc, p.w_sn, p.w_sk, a.f16);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
   a.Wt = Wt; a.n_atoms = g.n_atoms; a.n_rows_pad = g.n_rows_pad; a.NT = g.NT; a.tmem_cols = g.tmem_cols;
@@ -998,7 +1010,7 @@ cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspac
     int S = w_smem + stg_smem < budget ? (int)((budget - w_smem - stg_smem) / stage_bytes) : 0;
     if (S > kPipeMaxStages) S = kPipeMaxStages;
     bool pipe = S >= 2 && !getenv("DGS_SPCONV_NO_PIPE");
-    if (pipe && p.precision == SPCONV_BF16) {   // converted feature copy lives behind the weights in the workspace
+    if (pipe && p.precision != SPCONV_TF32) {   // converted (bf16 / fp16) feature copy lives behind the weights in the workspace
       uint8_t *feat = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(Wt + w_bytes) + 255) & ~(uintptr_t)255);
       const size_t f_bytes = (size_t)p.in_rows * g.k_pad * 2;
       if (feat + f_bytes > reinterpret_cast<uint8_t *>(workspace) + workspace_bytes) {
@@ -1006,7 +1018,7 @@ cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspac
       } else if (p.in_rows > 0) {
         const int64_t chunks = (int64_t)p.in_rows * (g.k_pad / 8);
         const int cb = (int)((chunks + 255) / 256 < 8192 ? (chunks + 255) / 256 : 8192);
-        spconv_to_bf16_kernel<<<cb, 256, 0, stream>>>(p.in, p.ld_in, p.in_rows, p.kdim, g.k_pad, reinterpret_cast<__nv_bfloat16 *>(feat));
+        spconv_to_bf16_kernel<<<cb, 256, 0, stream>>>(p.in, p.ld_in, p.in_rows, p.kdim, g.k_pad, reinterpret_cast<__nv_bfloat16 *>(feat), a.f16);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         a.feat = feat; a.feat_pitch = (int64_t)g.k_pad * 2; a.feat_valid_bytes = g.k_pad * 2;
       }

@@ -6,7 +6,7 @@
 
 namespace dgs {
 
-enum SpconvPrecision { SPCONV_FP32 = 0, SPCONV_TF32 = 1, SPCONV_BF16 = 2 };
+enum SpconvPrecision { SPCONV_FP32 = 0, SPCONV_TF32 = 1, SPCONV_BF16 = 2, SPCONV_FP16 = 3 };
 
 // One gather-GEMM-scatter pass:  out[omap[p], :ndim] += in[imap[p], :kdim] @ Wk   (Wk = kdim x ndim view of W[k])
 // The forward uses (kdim, ndim) = (c_in, c_out) with W[k][c][n]; the dX backward swaps the maps and uses

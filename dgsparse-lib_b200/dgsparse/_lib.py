@@ -15,7 +15,7 @@ _vp, _i32, _i64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_s
 
 SUM, MAX, MIN, MEAN = 0, 1, 2, 3                    # include/gspmm.h:13
 ADD, SUB, MUL, DIV, COPY, MASKMUL = 0, 1, 2, 3, 4, 5  # include/gspmm.h:14 (+ COPY / MASKMUL)
-SPCONV_FP32, SPCONV_TF32, SPCONV_BF16 = 0, 1, 2       # include/dgsparse_b200.h dgsSpconvPrecision
+SPCONV_FP32, SPCONV_TF32, SPCONV_BF16, SPCONV_FP16 = 0, 1, 2, 3       # include/dgsparse_b200.h dgsSpconvPrecision
 
 # every symbol include/*.h declares: (restype, argtypes)
 SIGNATURES = {

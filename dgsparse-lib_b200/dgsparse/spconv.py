@@ -5,28 +5,29 @@
 
 Same argument order and meaning as the reference.  `arch80=True` selects the tensor-core path (tcgen05
 kind::tf32, fp32 accumulate in TMEM; the reference's wmma tf32 kernels), `arch80=False` the exact fp32 FMA
-kernel (the reference's `_fgms_fusion_fp32*`).  `set_precision("bf16")` switches the tensor path to bf16
-operands.  Gradients flow to in_feats and kernel (src/spconv.cpp:43-62).
+kernel (the reference's `_fgms_fusion_fp32*`).  `set_precision("bf16" | "fp16")` switches the tensor path of fp32
+inputs to 16-bit operands.  Half inputs take tcgen05 kind::f16 with fp16 operands (the reference's fp16 wmma kernels,
+include/cuda/spconv.cuh:1408-1552: same 10-bit mantissa), bfloat16 inputs with bf16 operands; accumulation is fp32 in
+TMEM either way.  Gradients flow to in_feats and kernel (src/spconv.cpp:43-62).
 
-Fixes: out_feats is zero-initialised; `separate_mid` needs no cuBLAS; fp16 inputs are computed
-through the bf16 tensor path and returned in the input dtype instead of being written as half into an fp32
-buffer.
+Fixes: out_feats is zero-initialised; `separate_mid` needs no cuBLAS; half inputs are returned in the input
+dtype instead of being written as half into an fp32 buffer.
 """
 import torch
 
 from . import _lib
 from ._lib import check, lib, ptr, require_cuda, stream_of
 
-_PRECISION = {"fp32": _lib.SPCONV_FP32, "tf32": _lib.SPCONV_TF32, "bf16": _lib.SPCONV_BF16}
+_PRECISION = {"fp32": _lib.SPCONV_FP32, "tf32": _lib.SPCONV_TF32, "bf16": _lib.SPCONV_BF16, "fp16": _lib.SPCONV_FP16}
 _tensor_precision = _lib.SPCONV_TF32
 _ws = {}
 
 
 def set_precision(name):
-    """Operand precision of the tensor-core path used when arch80=True: "tf32" (default) or "bf16"."""
+    """Operand precision of the tensor-core path used when arch80=True: "tf32" (default), "bf16" or "fp16"."""
     global _tensor_precision
-    if name not in ("tf32", "bf16"):
-        raise ValueError("precision must be 'tf32' or 'bf16'")
+    if name not in ("tf32", "bf16", "fp16"):
+        raise ValueError("precision must be 'tf32', 'bf16' or 'fp16'")
     _tensor_precision = _PRECISION[name]
 
 
@@ -68,7 +69,9 @@ def _prep(in_feats, kernel, kpos, qkpos, in_map, out_map):
 
 
 def _precision_of(in_feats, arch80):
-    if in_feats.dtype in (torch.float16, torch.bfloat16):
+    if in_feats.dtype == torch.float16:
+        return _lib.SPCONV_FP16
+    if in_feats.dtype == torch.bfloat16:
         return _lib.SPCONV_BF16
     return _tensor_precision if arch80 else _lib.SPCONV_FP32
 

@@ -112,7 +112,7 @@ int dgs_edge_softmax(int M, int head, const int *rowptr, const float *values, fl
  * kind::tf32 with fp32 accumulation in TMEM (arch80 = true), DGS_SPCONV_BF16 = tcgen05 kind::f16 on bf16-rounded
  * operands.  Outputs are fully overwritten (the reference leaves out_feats uninitialised).
  * in_grad or kernel_grad may be NULL to skip that half of the backward.  kernel_grad is always fp32 FMA. */
-enum dgsSpconvPrecision { DGS_SPCONV_FP32 = 0, DGS_SPCONV_TF32 = 1, DGS_SPCONV_BF16 = 2 };
+enum dgsSpconvPrecision { DGS_SPCONV_FP32 = 0, DGS_SPCONV_TF32 = 1, DGS_SPCONV_BF16 = 2, DGS_SPCONV_FP16 = 3 };
 size_t dgs_spconv_workspace_bytes(int rows /* max(in_nnz, out_nnz) */, int k_vol, int c_in, int c_out, int precision);
 int dgs_spconv_fwd(int in_nnz, int out_nnz, int k_vol, int c_in, int c_out, const int *kpos, const int *qkpos,
                    const int *in_map, const int *out_map, int64_t sum_nnz, const float *in_feats, const float *kernel,

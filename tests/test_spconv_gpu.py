@@ -6,6 +6,7 @@ bounds the rounding error of a dot product rigorously):
   fp32  1e-5   (exact FMA; only the accumulation order differs: atomics)
   tf32  1.5e-3 (operands rounded to 10 mantissa bits: 2 * 2^-11 per product; the reference's own (disabled)
                check used rtol 1e-2, test/test_spconv.py:157-158)
+  fp16  1.5e-3 (operands rounded to 10 mantissa bits like tf32; inputs here are far inside the fp16 range)
   bf16  1.2e-2 (operands rounded to 7 mantissa bits: 2 * 2^-8 per product)
 """
 import os
@@ -16,7 +17,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TOL = {"fp32": 1e-5, "tf32": 1.5e-3, "bf16": 1.2e-2}
+TOL = {"fp32": 1e-5, "tf32": 1.5e-3, "fp16": 1.5e-3, "bf16": 1.2e-2}
 
 
 def dev(a):
@@ -67,7 +68,7 @@ def check(got, want, bound, precision, what):
                           f"max err/bound {float((err / (bound + 1e-30)).max()):.3e}"
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 @pytest.mark.parametrize("c_in,c_out", [(64, 64), (4, 64), (32, 96), (128, 32), (96, 256), (16, 16), (200, 72)])
 def test_forward_random_maps(precision, c_in, c_out):
     rng = np.random.default_rng(c_in * 1000 + c_out)
@@ -96,7 +97,7 @@ def test_forward_matches_c_oracle_small(oracle, precision):
 
 @pytest.mark.parametrize("separate", [False, True])
 @pytest.mark.parametrize("idx", [0, 1])
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_fixture_minkunet_layers(precision, idx, separate):
     """The reference's own kernel maps (example/data/sample-data/fp32/minkunet-semantickitti/*.pth re-saved as
     tests/golden/spconv_fp32_*.npz), driven exactly as test/test_spconv.py:100-147 does (random feats/weights)."""
@@ -201,3 +202,25 @@ def test_errors():
         S.spconv_fwd_fused(x, w, z, z, z, z, 10, 0, False, True)          # c_in mismatch, as the reference throws
     with pytest.raises(RuntimeError):
         S.spconv_fwd_fused(x.cpu(), torch.zeros(3, 8, 8), z, z, z, z, 10, 0, False, True)   # no CPU path
+
+
+@pytest.mark.parametrize("dtype,prec", [(torch.float16, "fp16"), (torch.bfloat16, "bf16")])
+def test_half_inputs_keep_their_operand_format(dtype, prec):
+    """Half tensors through the op boundary (test/test_spconv.py:100-147 with precision = 'fp16'): fp16 inputs are multiplied
+    as fp16 operands (tcgen05 kind::f16, like the reference's fp16 wmma kernels), bf16 inputs as bf16; fp32 accumulation; the
+    result comes back in the input dtype.  The already-rounded inputs make the products exact, so the only error left is the
+    accumulation order and the final rounding to the 16-bit output."""
+    import dgsparse  # noqa: F401  (registers torch.ops.dgsparse_spconv.spconv)
+    import dgsparse.spconv as S
+    rng = np.random.default_rng(11)
+    in_nnz, out_nnz, k_vol, c_in, c_out = 2000, 1800, 27, 64, 96
+    imap, omap, knnz = make_maps(rng, in_nnz, out_nnz, k_vol, 0.3)
+    x = torch.tensor(rng.uniform(-1, 1, (in_nnz, c_in)), dtype=torch.float32, device="cuda").to(dtype)
+    w = torch.tensor(rng.uniform(-1, 1, (k_vol, c_in, c_out)), dtype=torch.float32, device="cuda").to(dtype)
+    kpos, qkpos, sum_nnz = S.quantize_kpos(torch.from_numpy(knnz).cuda())
+    out = torch.ops.dgsparse_spconv.spconv(x, w, kpos, qkpos, dev(imap), dev(omap), out_nnz, sum_nnz, False, True)
+    assert out.dtype == dtype
+    want, bound = ref64(kpos.cpu().numpy(), imap, omap, x.float().cpu().numpy(), w.float().cpu().numpy(), out_nnz)
+    ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7          # rounding of the OUTPUT to 16 bits
+    err = np.abs(out.float().cpu().numpy().astype(np.float64) - want)
+    assert (err <= 1e-5 * bound + ulp * np.abs(want) + 1e-30).all(), float((err / (bound + 1e-30)).max())

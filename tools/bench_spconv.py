@@ -6,6 +6,9 @@
 Prints one JSON line per (layer, precision): forward / dX / dW device time (CUDA events, L2 flushed between
 repetitions), the algorithmic bytes (maps + each touched input row once + output once + weights) and the
 gather/scatter bytes that actually move through L2 (pairs * (c_in + c_out) * 4), and GFLOP/s = 2*pairs*c_in*c_out/t.
+Beside every tensor-core line: the REFERENCE'S OWN spconv_fwd_fused / spconv_bwd_fused (src/cuda/spconv_cuda.cu:18-253,
+compiled unmodified for sm_100a into oracle/_ref/_ref_spconv.so by oracle/build_ref_spconv.sh) on the same maps and
+tensors, same timing loop (`reference_*_ms`; its backward computes dX and dW in one call).
 """
 import argparse
 import json
@@ -41,6 +44,8 @@ def main():
     ap.add_argument("--channels", default="", help="extra c_in,c_out pairs on the layer-1 maps, e.g. 128,128;256,256")
     args = ap.parse_args()
     import dgsparse.spconv as S
+    from oracle import oracle
+    REF = oracle.ref_spconv_module()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     cases = []
     for idx in (0, 1):
@@ -67,10 +72,20 @@ def main():
                                                    precision=prec), args.reps, flush)
             dw = timeit(lambda: S.spconv_bwd_fused(go, x, w, kpos, qkpos, imap, omap, sum_nnz, False, True, need_in=False,
                                                    precision=prec), args.reps, flush)
-            print(json.dumps({"case": name, "precision": prec, "pairs": pairs, "c_in": c_in, "c_out": c_out,
-                              "fwd_ms": fwd, "dx_ms": dx, "dw_ms": dw, "fwd_gflops": flop / fwd / 1e6,
-                              "fwd_algorithmic_gbs": alg / fwd / 1e6,
-                              "fwd_gather_scatter_gbs": 4.0 * pairs * (c_in + c_out) / fwd / 1e6}))
+            line = {"case": name, "precision": prec, "pairs": pairs, "c_in": c_in, "c_out": c_out,
+                    "fwd_ms": fwd, "dx_ms": dx, "dw_ms": dw, "fwd_gflops": flop / fwd / 1e6,
+                    "fwd_algorithmic_gbs": alg / fwd / 1e6,
+                    "fwd_gather_scatter_gbs": 4.0 * pairs * (c_in + c_out) / fwd / 1e6}
+            if REF is not None and prec in ("fp32", "tf32"):
+                arch80 = prec == "tf32"
+                line["reference_fwd_ms"] = timeit(lambda: REF.spconv_fwd_fused(x, w, kpos, qkpos, imap, omap, out_nnz, sum_nnz, False, arch80),
+                                                  args.reps, flush)
+                if arch80:   # the reference's backward is tensor-core only (tf32 kernels whatever arch80 says)
+                    line["reference_bwd_dx_plus_dw_ms"] = timeit(
+                        lambda: REF.spconv_bwd_fused(go, x, w, kpos, qkpos, imap, omap, sum_nnz, False, True), args.reps, flush)
+                    line["ours_bwd_dx_plus_dw_ms"] = dx + dw
+                line["fwd_speedup_vs_reference"] = line["reference_fwd_ms"] / fwd
+            print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
