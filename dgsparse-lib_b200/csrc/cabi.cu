@@ -178,6 +178,7 @@ const char *dgs_last_error(void) { return g_err; }
 int dgs_sm_count(void) { return dgs::device_sm_count(); }
 int dgs_spmm_last_path(void) { return dgs::spmm_last_path(); }
 int dgs_set_option(const char *name, int value) { return dgs::set_option(name, value); }
+void dgs_spmm_forget_graph_notes(void) { dgs::spmm_forget_graph_notes(); }
 
 size_t dgs_spmm_workspace_bytes(int N, int64_t nnz, int with_arg) {
   return dgs::spmm_workspace_bytes(N, nnz, with_arg != 0);

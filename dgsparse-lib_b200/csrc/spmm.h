@@ -35,6 +35,7 @@ struct SpmmProblem {
 size_t spmm_workspace_bytes(int N, int64_t nnz, bool with_arg);
 cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 int device_sm_count();
+void spmm_forget_graph_notes();   // drop what the library remembers about matrices it has seen (tests, benchmarks)
 int spmm_last_path();   // which kernel family the calling thread's last spmm_csr launched: 0 row-segment (+ fix-up), 1 row-parallel
 
 // bench-only launch timing (see dgs_profile_enable in include/dgsparse_b200.h)

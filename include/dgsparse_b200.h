@@ -47,6 +47,9 @@ int dgs_set_option(const char *name, int value);
 /* Which kernel family the calling thread's last SpMM launched: 0 = row-segment kernel + fix-up (two launches, any matrix),
  * 1 = row-parallel single launch (latency regime, matrices the library has seen to have short rows only). */
 int dgs_spmm_last_path(void);
+/* Forget what the library has learnt about the matrices it has seen (which ones may take the row-parallel kernel):
+ * the next call on any matrix starts from the row-segment path again.  For tests and benchmarks. */
+void dgs_spmm_forget_graph_notes(void);
 
 /* The same with K = rows of B (columns of A) stated.  K only sizes the column panels (csrc/spmm.cu pick_panel): when a
  * 64-column panel of B, K x 256 B, would not stay L2-resident the feature axis is processed in narrower panels, one after
