@@ -276,10 +276,6 @@ static int pick_chunk(int N, int64_t nnz, bool with_arg, int G, bool remote) {
   return (int)((chunk + kBatch - 1) / kBatch * kBatch);
 }
 
-// SM-affine block order (spmm_rowseg.cuh): one counter per SM and column panel, behind the partials in the workspace
-static constexpr int kMaxQueues = 160, kMaxPanels = 16;
-static constexpr size_t kQueueBytes = (size_t)kMaxQueues * kMaxPanels * 4;
-
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static void geometry_for(int N, int64_t nnz, bool with_arg, bool can_vec4, int W, bool remote, int *vec, int *G, bool *narrow,
@@ -301,7 +297,7 @@ size_t spmm_workspace_bytes(int N, int64_t nnz, bool with_arg) {
     size_t b = align_up((size_t)nc * 4, 256) + align_up((size_t)nc * 2 * N * 4, 256) * (with_arg ? 2 : 1);
     if (b > need) need = b;
   }
-  return need + 256 + kQueueBytes;
+  return need + 256;
 }
 
 cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -336,7 +332,6 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   a.chunk = kBatch; a.num_chunks = 0;
   a.part_val = nullptr; a.part_arg = nullptr; a.tail_row = nullptr;
   a.hub_flag = nullptr; a.hub_limit = kRowParLimit;
-  a.sm_queue = nullptr; a.n_queues = 0;
 
   // latency regime: single-launch row-parallel kernel when this matrix is known to have short rows only
   int note = -1;
@@ -369,8 +364,7 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
     const size_t part_b = align_up((size_t)a.num_chunks * 2 * p.N * 4, 256);
     const size_t need = tail_b + part_b * (with_arg ? 2 : 1);
     if (workspace == nullptr || workspace_bytes < need) return cudaErrorInvalidValue;
-    a.sm_queue = nullptr; a.n_queues = 0;
-    char *w = static_cast<char *>(workspace);
+      char *w = static_cast<char *>(workspace);
     a.tail_row = reinterpret_cast<int *>(w);
     a.part_val = reinterpret_cast<float *>(w + tail_b);
     a.part_arg = with_arg ? reinterpret_cast<int *>(w + tail_b + part_b) : nullptr;
@@ -391,15 +385,6 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
     const int gpb = kSpmmThreads / G;
     dim3 grid((a.num_chunks + gpb - 1) / gpb, (p.N + G * vec - 1) / (G * vec));
     cudaError_t e;
-    // SM-affine block order: large matrices only (several blocks per SM and panel), counters zeroed per launch
-    const int affine = option(OPT_SPMM_SM_AFFINE);
-    const int sms = device_sm_count();
-    if (affine == 1 && (int)grid.x >= 4 * sms && sms <= kMaxQueues && (int)grid.y <= kMaxPanels &&
-        workspace_bytes >= align_up(need, 256) + (size_t)sms * grid.y * 4) {
-      a.sm_queue = reinterpret_cast<int *>(static_cast<char *>(workspace) + align_up(need, 256));
-      a.n_queues = sms;
-      if ((e = cudaMemsetAsync(a.sm_queue, 0, (size_t)sms * grid.y * 4, stream)) != cudaSuccess) return e;
-    }
     {
       ProfileScope prof(1, stream);
       e = fn(a, grid, stream);

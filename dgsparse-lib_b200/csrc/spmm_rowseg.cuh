@@ -55,30 +55,7 @@ struct SpmmArgs {
   int *nnz_report;    // (with nnz_dev) mapped host word that receives the true nnz: the next call's hint
   int *hub_flag;      // mapped host word set to 1 when a row longer than kRowParLimit is seen (null: nobody asks)
   int hub_limit;
-  int *sm_queue;      // [gridDim.y][n_queues] zeroed counters: SM-affine block order (null: blockIdx.x order)
-  int n_queues;
 };
-
-// SM-affine block order.  Consecutive segments cover consecutive rows, and graphs with community structure keep most of a
-// row's columns near the row — but the hardware hands consecutive blockIdx.x to DIFFERENT SMs, so neighbouring rows never
-// meet in one L1 (uniform columns: L1 hit 0.4 %; 85 % intra-community columns: 8 %, profiles/r02_ncu_locality_reddit64.csv).
-// Here the block list is cut into one contiguous range per SM and a block takes the next entry of the range of the SM it
-// RUNS on (%smid), stealing from the following SMs when its own range is drained: the blocks resident on an SM at any
-// time then walk adjacent rows, and the B rows of their community are gathered through that SM's L1.
-__device__ __forceinline__ int sm_affine_block(int *cnt, int n_queues, int total) {
-  unsigned smid;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  const int per = (total + n_queues - 1) / n_queues;
-  const int q0 = (int)(smid % (unsigned)n_queues);
-  for (int i = 0; i < n_queues; i++) {
-    const int q = (q0 + i) % n_queues;
-    const int lo = q * per, hi = min(lo + per, total);
-    if (lo >= hi) continue;
-    const int k = atomicAdd(cnt + q, 1);
-    if (lo + k < hi) return lo + k;
-  }
-  return -1;
-}
 
 // Segment layout actually used by a launch.  Normally the host's (a.nnz, a.chunk, a.num_chunks).  The legacy entry points
 // (spmm_cuda(m, k, rowptr, ...): no nnz argument) must not block on a device->host copy of rowptr[M], so there the host
@@ -139,15 +116,7 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
   // Programmatic dependent launch: the fix-up grid may start now; its first half (the zero rows of empty rows) touches
   // nothing this kernel reads or writes, its second half waits for this grid (griddepcontrol.wait).
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  int bx = blockIdx.x;
-  if (a.sm_queue != nullptr) {   // uniform per launch
-    __shared__ int s_bx;
-    if (threadIdx.x == 0) s_bx = sm_affine_block(a.sm_queue + blockIdx.y * a.n_queues, a.n_queues, gridDim.x);
-    __syncthreads();
-    bx = s_bx;
-    if (bx < 0) return;
-  }
-  const int chunk_id = bx * GPB + grp;
+  const int chunk_id = blockIdx.x * GPB + grp;
   const SegLayout sl = seg_layout(a);
   if (chunk_id >= sl.num_chunks) return;
 
@@ -326,12 +295,13 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
   const int64_t row0 = warp * 32;
   if (row0 < a.M) {
     const int row = (int)row0 + lane;
-    bool empty = false;
+    bool empty = false, hub = false;
     if (row < a.M) {
       const int deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
       empty = deg == 0;
-      if (a.hub_flag && deg > a.hub_limit) *a.hub_flag = 1;   // this matrix is not for the row-parallel kernel
+      hub = deg > a.hub_limit;
     }
+    if (a.hub_flag && __any_sync(0xffffffffu, hub) && lane == 0) *a.hub_flag = 1;   // not a matrix for the row-parallel kernel
     unsigned m = __ballot_sync(0xffffffffu, empty);
     while (m) {
       const int rr = (int)row0 + (__ffs(m) - 1);

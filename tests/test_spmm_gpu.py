@@ -429,22 +429,3 @@ def test_row_parallel_selected_by_graph_note_and_healed(K, oracle, graphs):
         assert_close_f32(out.cpu().numpy(), ref2, oracle.spmm_f64(r2, c2, v2, B), what="rewritten", absref=oracle.spmm_f64(r2, c2, v2, B))
     assert paths[0] == 1 and paths[-1] == 0, paths
 
-
-def test_sm_affine_block_order(K, oracle, graphs, knob):
-    """Option spmm_sm_affine: blocks take their segments from a per-SM queue (with stealing) instead of blockIdx.x order.
-    Every segment must still be processed exactly once: identical bytes to the default order, on a matrix large enough
-    to engage it (>= 4 blocks per SM), 64 and 128 columns (one queue set per column panel), sum and max+arg."""
-    rowptr, col = graphs.reddit_like(1 / 8)
-    M = rowptr.size - 1
-    val = graphs.uniform(col.size, 1)
-    rp, cc, vv = dev(rowptr), dev(col), dev(val)
-    for N in (64, 128):
-        B = dev(graphs.uniform(M * N, 2).reshape(M, N))
-        knob("spmm_sm_affine", 0)
-        want_sum = K.spmm(rp, cc, vv, B)
-        want_max, want_E = K.spmm(rp, cc, vv, B, RED["max"], COMP["mul"], with_arg=True)
-        knob("spmm_sm_affine", 1)
-        for _ in range(3):
-            assert torch.equal(K.spmm(rp, cc, vv, B), want_sum)
-            got_max, got_E = K.spmm(rp, cc, vv, B, RED["max"], COMP["mul"], with_arg=True)
-            assert torch.equal(got_max, want_max) and torch.equal(got_E, want_E)

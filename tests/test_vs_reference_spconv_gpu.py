@@ -209,7 +209,6 @@ def test_backward_same_as_reference(REF, arch80):
     wt = np.ascontiguousarray(np.transpose(w, (0, 2, 1)))
     want_in, bound_in = ref64(g["kpos"], g["omap"], g["imap"], go, wt, in_nnz)
     check(o_gin.cpu().numpy(), want_in, bound_in, "tf32", "ours dX")
-    check(t_gin.cpu().numpy(), want_in, bound_in, "tf32", "reference dX")
     kp = g["kpos"]
     want_w = np.zeros((k_vol, c_in, c_out))
     bound_w = np.zeros_like(want_w)
@@ -219,4 +218,16 @@ def test_backward_same_as_reference(REF, arch80):
         want_w[k] = a.T @ b
         bound_w[k] = np.abs(a).T @ np.abs(b)
     check(o_gw.cpu().numpy(), want_w, bound_w, "tf32", "ours dW")
-    check(t_gw.cpu().numpy(), want_w, bound_w, "tf32", "reference dW")
+    # The reference's backward has no test of its own (test/test_spconv.py never calls it).  Measured here on B200, built
+    # unmodified: its dX (_fgms_fusion_tf32_W_transpose, include/cuda/spconv.cuh:1876+) does NOT agree with fp64 on this
+    # 64 -> 64 layer (about half of the elements off by O(1) of their bound).  Where the reference is right ours must agree
+    # with it; where it is wrong the finding is printed (pytest -s) and recorded in DESIGN.md §8, not mirrored.
+    report = {}
+    for name, theirs, ours_t, want, bound in (("dX", t_gin, o_gin, want_in, bound_in), ("dW", t_gw, o_gw, want_w, bound_w)):
+        err = np.abs(theirs.cpu().numpy().astype(np.float64) - want)
+        frac_bad = float((err > TOL["tf32"] * bound + 1e-30).mean())
+        report[name] = frac_bad
+        if frac_bad == 0.0:
+            d = np.abs(ours_t.cpu().numpy().astype(np.float64) - theirs.cpu().numpy())
+            assert (d <= 2 * TOL["tf32"] * bound + 1e-30).all(), name
+    print("reference backward, fraction of elements outside the tf32 bound of the fp64 oracle:", report)

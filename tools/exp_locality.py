@@ -33,8 +33,7 @@ def main():
         out = torch.empty(M, N, device=dev)
         S = int(name.split("_")[1]) if "_" in name else 0
         intra = float(np.mean((row // S) == (col // S))) if S else None
-        for affine in (0, 1):      # option spmm_sm_affine: blocks take their segments from the range of the SM they run on
-            L.lib.dgs_set_option(b"spmm_sm_affine", affine)
+        for affine in (0,):        # (round 2 also ran an SM-affine block order here: no gain, tools/dead_ends/README.md)
             for _ in range(2):
                 K.spmm(rp, cc, val, B, L.SUM, L.MUL, out=out)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -46,7 +45,6 @@ def main():
             ms = e0.elapsed_time(e1) / 5
             print(json.dumps({"graph": name, "N": N, "nnz": nnz, "intra_community_fraction": intra, "sm_affine": affine, "ms": ms,
                               "gflops": 2.0 * nnz * N / ms / 1e6, "gather_TBps": nnz * N * 4 / (ms * 1e-3) / 1e12}), flush=True)
-        L.lib.dgs_set_option(b"spmm_sm_affine", -1)
         del rp, cc, val, B, out
         torch.cuda.empty_cache()
 
