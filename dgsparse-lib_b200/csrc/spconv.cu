@@ -638,6 +638,96 @@ __global__ void __launch_bounds__(256) spconv_fgms_simt_kernel(const SpconvArgs 
   }
 }
 
+// ---- exact fp32, tiled: the path arch80 = false takes whenever rows are 16-byte aligned ---------------------------------
+// The warp-per-4-pairs kernel above re-reads W[k] for every 4 pairs and runs at ~3 TFLOP/s (0.82 ms on the MinkUNet 64 -> 64
+// layer, where the reference's _fgms_fusion_fp32 takes 0.10 ms on the same B200: profiles/r02_spconv_vs_reference.jsonl).
+// This one is a plain register-blocked SGEMM on gathered tiles: a CTA of 256 threads owns one tile of 128 pairs (one offset)
+// x 64 output channels and walks c_in in chunks of 32: the gathered rows go to shared memory TRANSPOSED (channel-major, so
+// that a thread reads its 8 pairs of one channel with two 16-byte loads), the W[k] chunk row-major; thread (ty, tx)
+// accumulates an 8 x 4 block with fp32 FMAs, c_in ascending (the order of cpu_compute), and the block is scattered with
+// red.global.add.v4.f32.  32 FMAs per 3 shared-memory loads; several CTAs per SM hide the gather.
+constexpr int kFtN = 64, kFtK = 32, kFtLdA = kTileM + 4;
+__global__ void __launch_bounds__(256) spconv_fgms_fp32_tiled_kernel(const SpconvArgs a, const float *__restrict__ W, int64_t w_sc,
+                                                                     int64_t w_sn, int64_t w_sk, int out_vec4) {
+  __shared__ __align__(16) float sA[kFtK][kFtLdA];
+  __shared__ __align__(16) float sW[kFtK][kFtN];
+  __shared__ int s_in[kTileM], s_out[kTileM];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tile = blockIdx.x, co0 = blockIdx.y * kFtN;
+  int k;
+  if (tile < a.n_map_tiles) {
+    const int q0 = tile * kTileM;
+    k = upper_bound_i32(a.qkpos, a.k_vol + 1, q0) - 1;
+    const int p0 = q0 - __ldg(a.qkpos + k) + __ldg(a.kpos + k), pe = __ldg(a.kpos + k + 1);
+    if (tid < kTileM) {
+      const bool ok = p0 + tid < pe;
+      s_in[tid] = ok ? __ldg(a.imap + p0 + tid) : -1;
+      s_out[tid] = ok ? __ldg(a.omap + p0 + tid) : -1;
+    }
+  } else {
+    k = a.mid_k;
+    const int r0 = (tile - a.n_map_tiles) * kTileM;
+    if (tid < kTileM) s_in[tid] = s_out[tid] = r0 + tid < a.id_rows ? r0 + tid : -1;
+  }
+  __syncthreads();
+  const float *Wk = W + (int64_t)k * w_sk;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+
+  const int g_row = tid & (kTileM - 1), g_half = tid >> 7;   // gather: thread -> (pair, 16 of the chunk's 32 channels)
+  const int my_in = s_in[g_row];
+  for (int c0 = 0; c0 < a.c_in; c0 += kFtK) {
+    // A chunk, transposed into shared memory (rows of 128 consecutive pairs: conflict-free stores)
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      const int ch = c0 + g_half * 16 + v * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (my_in >= 0 && ch < a.c_in) x = __ldg(reinterpret_cast<const float4 *>(a.in + (int64_t)my_in * a.ld_in + ch));   // c_in % 4 == 0
+      const int cl = g_half * 16 + v * 4;
+      sA[cl + 0][g_row] = x.x; sA[cl + 1][g_row] = x.y; sA[cl + 2][g_row] = x.z; sA[cl + 3][g_row] = x.w;
+    }
+    // W chunk [32][64] (any strides: the dX pass reads W transposed)
+#pragma unroll
+    for (int v = 0; v < (kFtK * kFtN) / 256; v++) {
+      const int e = v * 256 + tid, ci = e / kFtN, co = e % kFtN;
+      float w = 0.0f;
+      if (c0 + ci < a.c_in && co0 + co < a.c_out) w = __ldg(Wk + (int64_t)(c0 + ci) * w_sc + (int64_t)(co0 + co) * w_sn);
+      sW[ci][co] = w;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int ci = 0; ci < kFtK; ci++) {
+      const float4 a0 = *reinterpret_cast<const float4 *>(&sA[ci][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4 *>(&sA[ci][ty * 8 + 4]);
+      const float4 w = *reinterpret_cast<const float4 *>(&sW[ci][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const int co = co0 + tx * 4;
+  if (co >= a.c_out) return;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int orow = s_out[ty * 8 + i];
+    if (orow < 0) continue;
+    float *dst = a.out + (int64_t)orow * a.ld_out + co;
+    if (out_vec4) red_add_v4(dst, acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    else {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (co + j < a.c_out) atomicAdd(dst + j, acc[i][j]);
+    }
+  }
+}
+
 // ---- kernel gradient: dW[k][ci][co] = sum over the pairs p of offset k of in[imap[p]][ci] * dout[omap[p]][co] ----------
 // (_fgms_fusion_tf32_I_transpose of the reference, src/cuda/spconv_cuda.cu:241-247.)  A CTA of 16 x 16 threads owns a
 // 64 x 64 block of dW and a run of pair tiles; per tile it stages the gathered 128 x 64 panels of `in` and `dout` in
@@ -981,6 +1071,14 @@ cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspac
                      (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
   if (p.precision == SPCONV_FP32 || !tc_ok) {
     a.Wt = nullptr; a.n_atoms = 0; a.n_rows_pad = 0; a.NT = 0; a.tmem_cols = 0; a.tiles_per_cta = 1;
+    // register-blocked tiled kernel when the gathered rows can be read as float4; the warp-per-4-pairs kernel otherwise
+    const bool in_vec4 = p.kdim % 4 == 0 && p.ld_in % 4 == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
+    if (in_vec4 && !getenv("DGS_SPCONV_FP32_SIMPLE")) {
+      const int out_vec4 = p.ndim % 4 == 0 && p.ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+      dim3 grid(n_tiles, (p.ndim + kFtN - 1) / kFtN);
+      spconv_fgms_fp32_tiled_kernel<<<grid, 256, 0, stream>>>(a, p.W, p.w_sc, p.w_sn, p.w_sk, out_vec4);
+      return cudaGetLastError();
+    }
     const int64_t warps = (int64_t)n_tiles * (kTileM / kSimtPairs);
     const int blocks = (int)((warps * 32 + 255) / 256);
     spconv_fgms_simt_kernel<<<blocks, 256, 0, stream>>>(a, p.W, p.w_sc, p.w_sn, p.w_sk);
