@@ -243,19 +243,18 @@ static void pick_geometry(int N, int W, bool can_vec4, int *vec, int *G, bool *n
 static constexpr size_t kWorkspaceCap = 192u << 20;
 // Segments per resident lane group: more segments = finer dynamic balance through the block scheduler, fewer = fewer rows
 // cut by a segment boundary (those are finished by the fix-up kernel, which on N GPUs is an NVLink-ingress burst).
-// Measured on B200 (DGS_SPMM_SEGS sweep): the main kernel does not care (reddit@64 1.573 / 1.568 / 1.567 / 1.570 / 1.575 ms
-// for 8 / 4 / 3 / 2 / 1, products@128 8.95 / 8.93 / 8.95 ms for 8 / 4 / 3) while the fix-up shrinks from 0.018 to 0.013 ms.
-// remote = the epilogue also stores to other GPUs (peer pointers or the NVLS multicast address): one segment per resident
-// group, so that as few rows as possible are cut and finished by the fix-up grid's burst over NVLink.
-static int segs_per_group(bool remote) {
+// Measured on B200 (option spmm_segs): the main kernel does not care (reddit@64 1.573 / 1.568 / 1.567 / 1.570 / 1.575 ms
+// for 8 / 4 / 3 / 2 / 1, products@128 8.95 / 8.93 / 8.95 ms for 8 / 4 / 3) while the fix-up shrinks with the segment count.
+// 2 everywhere — the SAME layout whether the epilogue stores locally or fans out to other GPUs, so that the column-sharded
+// result stays bit-identical to the single-GPU one (rows are folded at the same places).
+static int segs_per_group() {
   const int v = option(OPT_SPMM_SEGS);
-  if (v >= 1 && v <= 64) return v;
-  return remote ? 1 : 4;
+  return (v >= 1 && v <= 64) ? v : 2;
 }
 
-static int pick_chunk(int N, int64_t nnz, bool with_arg, int G, bool remote) {
+static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
   const int64_t resident_groups = (int64_t)device_sm_count() * 3 * (kSpmmThreads / G);
-  const int spg = segs_per_group(remote);
+  const int spg = segs_per_group();
   int64_t chunk = (nnz + resident_groups * spg - 1) / (resident_groups * spg);
   // Small matrices (latency regime): one 32-nnz batch per segment spreads them over more SMs; with two or more column
   // panels (N > 64) the extra cut rows cost more than that buys.  p2p-Gnutella31 / ca-CondMat, us per call, min 32 | 64 | 128:
@@ -278,10 +277,10 @@ static int pick_chunk(int N, int64_t nnz, bool with_arg, int G, bool remote) {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static void geometry_for(int N, int64_t nnz, bool with_arg, bool can_vec4, int W, bool remote, int *vec, int *G, bool *narrow,
+static void geometry_for(int N, int64_t nnz, bool with_arg, bool can_vec4, int W, int *vec, int *G, bool *narrow,
                          int *chunk, int *num_chunks) {
   pick_geometry(N, W, can_vec4, vec, G, narrow);
-  *chunk = pick_chunk(N, nnz, with_arg, *G, remote);
+  *chunk = pick_chunk(N, nnz, with_arg, *G);
   *num_chunks = (int)((nnz + *chunk - 1) / *chunk);
 }
 
@@ -293,7 +292,7 @@ size_t spmm_workspace_bytes(int N, int64_t nnz, bool with_arg) {
     static const int widths[3] = {64, 32, 64};
     int vec, G, chunk, nc;
     bool narrow;
-    geometry_for(N, nnz, with_arg, pass < 2, widths[pass], false, &vec, &G, &narrow, &chunk, &nc);   // local: the most segments
+    geometry_for(N, nnz, with_arg, pass < 2, widths[pass], &vec, &G, &narrow, &chunk, &nc);
     size_t b = align_up((size_t)nc * 4, 256) + align_up((size_t)nc * 2 * N * 4, 256) * (with_arg ? 2 : 1);
     if (b > need) need = b;
   }
@@ -359,7 +358,7 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   g_last_path = 0;
   if (p.nnz > 0) {
     const int W = pick_panel(p.N, p.K > 0 ? p.K : p.M, false);
-    geometry_for(p.N, p.nnz, with_arg, can_vec4, W, p.n_dst > 1 || p.mcast != 0, &vec, &G, &narrow, &a.chunk, &a.num_chunks);
+    geometry_for(p.N, p.nnz, with_arg, can_vec4, W, &vec, &G, &narrow, &a.chunk, &a.num_chunks);
     const size_t tail_b = align_up((size_t)a.num_chunks * 4, 256);
     const size_t part_b = align_up((size_t)a.num_chunks * 2 * p.N * 4, 256);
     const size_t need = tail_b + part_b * (with_arg ? 2 : 1);
