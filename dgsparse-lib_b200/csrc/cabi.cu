@@ -478,6 +478,137 @@ int dgs_spmm_csr_host(int M, int K, int N, int64_t nnz, const int *rowptr, const
   return ok_or(cudaStreamSynchronize(s_in), "dgs_spmm_csr_host(sync in)");
 }
 
+// ---- resident CSR: upload the matrix once, multiply many times from host memory -----------------------------------
+// The real GNN use of the host path: A is fixed across layers / epochs, B changes every step.  dgs_spmm_csr_host re-sends
+// 977 of its 1 037 MB (reddit@64) on every call; here the CSR crosses PCIe once (dgs_csr_upload), and a step moves only B
+// in and C out.  A step: B host->device, then the row blocks of A (equal nnz) are multiplied one after the other while the
+// finished rows of C are already on their way back (three streams, as in dgs_spmm_csr_host).
+namespace {
+struct ResidentCsr {
+  int device = 0, M = 0, K = 0, nblk = 0;
+  int64_t nnz = 0;
+  bool has_val = false;
+  int r_begin[17] = {0};
+  int64_t p_begin[17] = {0};
+  char *base = nullptr;          // one allocation: per-block rebased rowptr copies | col | val
+  int *rowptr = nullptr, *col = nullptr;
+  float *val = nullptr;
+  char *scratch = nullptr;       // B | C | E | workspace for the current N (grown on demand)
+  size_t scratch_bytes = 0;
+  cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_done[16] = {nullptr};
+};
+}  // namespace
+
+int dgs_csr_upload(int M, int K, int64_t nnz, const int *rowptr, const int *col, const float *val, void **handle) {
+  if (M <= 0 || K <= 0 || nnz < 0 || rowptr == nullptr || (nnz > 0 && col == nullptr) || handle == nullptr)
+    return fail(cudaErrorInvalidValue, "dgs_csr_upload(arguments)");
+  ResidentCsr *h = new ResidentCsr();
+  cudaError_t e = cudaGetDevice(&h->device);
+  if (e != cudaSuccess) { delete h; return fail(e, "dgs_csr_upload(device)"); }
+  h->M = M; h->K = K; h->nnz = nnz; h->has_val = val != nullptr;
+  int nblk = (int)(nnz / (8ll << 20));   // >= ~8 M nonzeros per block, as the per-call host path
+  if (nblk < 1) nblk = 1;
+  if (nblk > 16) nblk = 16;
+  if (nblk > M) nblk = M;
+  h->nblk = nblk;
+  for (int b = 1; b < nblk; b++) {
+    const int64_t target = nnz * b / nblk;
+    int lo = h->r_begin[b - 1], hi = M;
+    while (lo < hi) {
+      const int mid = lo + (hi - lo) / 2;
+      if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    h->r_begin[b] = lo;
+  }
+  h->r_begin[nblk] = M;
+  for (int b = 0; b <= nblk; b++) h->p_begin[b] = rowptr[h->r_begin[b]];
+  const size_t b_rowptr = up256(4 * ((size_t)M + 1 + nblk)), b_col = up256(4 * (size_t)nnz), b_val = h->has_val ? b_col : 0;
+  auto bail = [&](cudaError_t err, const char *where) {
+    if (h->base) cudaFree(h->base);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_k) cudaStreamDestroy(h->s_k);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    delete h;
+    return fail(err, where);
+  };
+  if ((e = cudaMalloc((void **)&h->base, b_rowptr + b_col + b_val + 256)) != cudaSuccess) return bail(e, "dgs_csr_upload(alloc)");
+  h->rowptr = (int *)h->base; h->col = (int *)(h->base + b_rowptr); h->val = h->has_val ? (float *)(h->base + b_rowptr + b_col) : nullptr;
+  if ((e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "dgs_csr_upload(stream)");
+  if ((e = cudaStreamCreateWithFlags(&h->s_k, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "dgs_csr_upload(stream)");
+  if ((e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "dgs_csr_upload(stream)");
+  if ((e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "dgs_csr_upload(event)");
+  for (int i = 0; i < 16; i++)
+    if ((e = cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "dgs_csr_upload(event)");
+  for (int b = 0; b < nblk; b++) {   // block b's rowptr copy holds rows + 1 entries, rebased to the block's first nonzero
+    const int r0 = h->r_begin[b], rows = h->r_begin[b + 1] - r0;
+    int *d_rp = h->rowptr + r0 + b;
+    if ((e = cudaMemcpyAsync(d_rp, rowptr + r0, 4 * ((size_t)rows + 1), cudaMemcpyHostToDevice, h->s_in)) != cudaSuccess) return bail(e, "dgs_csr_upload(h2d rowptr)");
+    if (h->p_begin[b] != 0) rebase_rowptr_kernel<<<(rows + 1 + 255) / 256, 256, 0, h->s_in>>>(d_rp, rows + 1, (int)h->p_begin[b]);
+  }
+  if (nnz > 0) {
+    if ((e = cudaMemcpyAsync(h->col, col, 4 * (size_t)nnz, cudaMemcpyHostToDevice, h->s_in)) != cudaSuccess) return bail(e, "dgs_csr_upload(h2d col)");
+    if (h->has_val && (e = cudaMemcpyAsync(h->val, val, 4 * (size_t)nnz, cudaMemcpyHostToDevice, h->s_in)) != cudaSuccess) return bail(e, "dgs_csr_upload(h2d val)");
+  }
+  if ((e = cudaStreamSynchronize(h->s_in)) != cudaSuccess) return bail(e, "dgs_csr_upload(sync)");
+  *handle = h;
+  return 0;
+}
+
+int dgs_csr_free(void *handle) {
+  ResidentCsr *h = static_cast<ResidentCsr *>(handle);
+  if (h == nullptr) return 0;
+  cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->s_k); cudaStreamSynchronize(h->s_out);
+  if (h->scratch) cudaFree(h->scratch);
+  if (h->base) cudaFree(h->base);
+  cudaEventDestroy(h->ev_in);
+  for (int i = 0; i < 16; i++) cudaEventDestroy(h->ev_done[i]);
+  cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_k); cudaStreamDestroy(h->s_out);
+  delete h;
+  return 0;
+}
+
+int dgs_spmm_csr_resident_host(void *handle, int N, const float *B, float *C, int *E, int reduce, int compute) {
+  ResidentCsr *h = static_cast<ResidentCsr *>(handle);
+  if (h == nullptr || N <= 0 || B == nullptr || C == nullptr) return fail(cudaErrorInvalidValue, "dgs_spmm_csr_resident_host(arguments)");
+  const bool with_arg = E != nullptr;
+  size_t ws_need = 256;
+  for (int b = 0; b < h->nblk; b++) {
+    const size_t w = dgs::spmm_workspace_bytes(N, h->p_begin[b + 1] - h->p_begin[b], with_arg);
+    if (w > ws_need) ws_need = w;
+  }
+  const size_t b_B = up256(4 * (size_t)h->K * N), b_C = up256(4 * (size_t)h->M * N), b_E = with_arg ? b_C : 0, b_ws = up256(ws_need);
+  cudaError_t e;
+  if (h->scratch_bytes < b_B + b_C + b_E + b_ws) {
+    if (h->scratch) { cudaStreamSynchronize(h->s_k); cudaStreamSynchronize(h->s_out); cudaFree(h->scratch); h->scratch = nullptr; h->scratch_bytes = 0; }
+    if ((e = cudaMalloc((void **)&h->scratch, b_B + b_C + b_E + b_ws)) != cudaSuccess) return fail(e, "dgs_spmm_csr_resident_host(alloc)");
+    h->scratch_bytes = b_B + b_C + b_E + b_ws;
+  }
+  float *d_B = (float *)h->scratch, *d_C = (float *)(h->scratch + b_B);
+  int *d_E = with_arg ? (int *)(h->scratch + b_B + b_C) : nullptr;
+  void *d_ws = h->scratch + b_B + b_C + b_E;
+  if ((e = cudaMemcpyAsync(d_B, B, 4 * (size_t)h->K * N, cudaMemcpyHostToDevice, h->s_in)) != cudaSuccess) return fail(e, "h2d B");
+  if ((e = cudaEventRecord(h->ev_in, h->s_in)) != cudaSuccess) return fail(e, "event record");
+  if ((e = cudaStreamWaitEvent(h->s_k, h->ev_in, 0)) != cudaSuccess) return fail(e, "event wait");
+  for (int b = 0; b < h->nblk; b++) {
+    const int r0 = h->r_begin[b], rows = h->r_begin[b + 1] - r0;
+    const int64_t p0 = h->p_begin[b], n = h->p_begin[b + 1] - p0;
+    if (rows > 0) {
+      int rc = dgs_spmm_csr_k(rows, h->K, N, n, h->rowptr + r0 + b, h->col + p0, h->val ? h->val + p0 : nullptr, d_B, N,
+                              d_C + (size_t)r0 * N, N, d_E ? d_E + (size_t)r0 * N : nullptr, N, reduce, compute, d_ws, b_ws, h->s_k);
+      if (rc) return rc;
+    }
+    if ((e = cudaEventRecord(h->ev_done[b], h->s_k)) != cudaSuccess) return fail(e, "event record");
+    if ((e = cudaStreamWaitEvent(h->s_out, h->ev_done[b], 0)) != cudaSuccess) return fail(e, "event wait");
+    if (rows > 0) {
+      if ((e = cudaMemcpyAsync(C + (size_t)r0 * N, d_C + (size_t)r0 * N, 4 * (size_t)rows * N, cudaMemcpyDeviceToHost, h->s_out)) != cudaSuccess) return fail(e, "d2h C");
+      if (with_arg && (e = cudaMemcpyAsync(E + (size_t)r0 * N, d_E + (size_t)r0 * N, 4 * (size_t)rows * N, cudaMemcpyDeviceToHost, h->s_out)) != cudaSuccess) return fail(e, "d2h E");
+    }
+  }
+  if ((e = cudaStreamSynchronize(h->s_out)) != cudaSuccess) return fail(e, "dgs_spmm_csr_resident_host(sync out)");
+  return ok_or(cudaStreamSynchronize(h->s_k), "dgs_spmm_csr_resident_host(sync compute)");
+}
+
 int dgs_sddmm_csr_host(int M, int Kdim, int ncols, int64_t nnz, const int *rowptr, const int *col, const float *D1,
                        const float *D2, float *out) {
   if (M < 0 || Kdim < 0 || ncols < 0 || nnz < 0) return fail(cudaErrorInvalidValue, "dgs_sddmm_csr_host(sizes)");

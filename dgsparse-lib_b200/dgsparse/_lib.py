@@ -56,6 +56,9 @@ SIGNATURES = {
     "dgs_ipc_close": (_i32, [_vp]),
     "dgs_profile_enable": (_i32, [_i32]),
     "dgs_profile_collect": (_i32, [_i32, _vp, _vp]),
+    "dgs_csr_upload": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_void_p)]),
+    "dgs_spmm_csr_resident_host": (_i32, [_vp, _i32, _vp, _vp, _vp, _i32, _i32]),
+    "dgs_csr_free": (_i32, [_vp]),
     "dgs_spmm_csr_host": (_i32, [_i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32]),
     "dgs_sddmm_csr_host": (_i32, [_i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
     # legacy dgSPARSE symbols (include/dgsparse.h)

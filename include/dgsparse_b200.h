@@ -181,6 +181,13 @@ int dgs_profile_collect(int max_records, int *kernel_ids, float *ms);
  * cached per thread between calls. */
 int dgs_spmm_csr_host(int M, int K, int N, int64_t nnz, const int *rowptr, const int *col, const float *val,
                       const float *B, float *C, int *E, int reduce, int compute);
+/* The same for a matrix that stays the same across calls (a GNN's adjacency): dgs_csr_upload copies the host CSR to the
+ * device ONCE and returns a handle; dgs_spmm_csr_resident_host then moves only B (host [K, N]) in and C (host [M, N], and E)
+ * out per call, the row blocks of A multiplied while the finished rows of C are already crossing PCIe.  Synchronises before
+ * returning.  One handle is used by one thread at a time. */
+int dgs_csr_upload(int M, int K, int64_t nnz, const int *rowptr, const int *col, const float *val /* may be NULL */, void **handle);
+int dgs_spmm_csr_resident_host(void *handle, int N, const float *B, float *C, int *E /* may be NULL */, int reduce, int compute);
+int dgs_csr_free(void *handle);
 int dgs_sddmm_csr_host(int M, int Kdim, int ncols, int64_t nnz, const int *rowptr, const int *col, const float *D1,
                        const float *D2, float *out);
 

@@ -429,3 +429,38 @@ def test_row_parallel_selected_by_graph_note_and_healed(K, oracle, graphs):
         assert_close_f32(out.cpu().numpy(), ref2, oracle.spmm_f64(r2, c2, v2, B), what="rewritten", absref=oracle.spmm_f64(r2, c2, v2, B))
     assert paths[0] == 1 and paths[-1] == 0, paths
 
+
+
+def test_resident_csr_host_entry(oracle, graphs):
+    """dgs_csr_upload + dgs_spmm_csr_resident_host: the CSR crosses PCIe once, every call moves only B in and C (and E) out.
+    Several B's, two feature widths (the device scratch regrows), sum and max + arg, a matrix large enough for several row
+    blocks with empty rows at block boundaries; results must equal the per-call host entry's."""
+    import dgsparse._lib as L
+    rowptr, col = graphs.reddit_like(1 / 4)          # 28.6 M nnz -> 3 row blocks
+    M = rowptr.size - 1
+    val = graphs.uniform(col.size, 1, 0.5, 1.5)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    h = ctypes.c_void_p()
+    L.check(L.lib.dgs_csr_upload(M, M, col.size, p(rowptr), p(col), p(val), ctypes.byref(h)), "dgs_csr_upload")
+    try:
+        for N, seed in ((64, 2), (32, 3), (64, 4)):
+            B = graphs.uniform(M * N, seed, -1, 1).reshape(M, N)
+            C = np.full((M, N), np.nan, np.float32)
+            L.check(L.lib.dgs_spmm_csr_resident_host(h, N, p(B), p(C), None, 0, 2), "resident sum")
+            want = np.empty((M, N), np.float32)
+            L.check(L.lib.dgs_spmm_csr_host(M, M, N, col.size, p(rowptr), p(col), p(val), p(B), p(want), None, 0, 2), "host sum")
+            assert np.array_equal(C, want)                       # same kernels, same row blocks
+            rows = np.unique(np.concatenate([np.arange(0, M, 997), np.argsort(np.diff(rowptr))[-4:]]))
+            sub_rp = np.concatenate([[0], np.cumsum(np.diff(rowptr)[rows])]).astype(np.int32)
+            sub_idx = np.concatenate([np.arange(rowptr[r], rowptr[r + 1]) for r in rows])
+            ref64 = oracle.spmm_f64(sub_rp, col[sub_idx], val[sub_idx], B)
+            assert_close_f32(C[rows], oracle.spmm(sub_rp, col[sub_idx], val[sub_idx], B), ref64, what=f"resident N={N}",
+                             absref=spmm_absref(oracle, sub_rp, col[sub_idx], val[sub_idx], B))
+        N = 64
+        B = graphs.uniform(M * N, 9, -1, 1).reshape(M, N)
+        C, E = np.empty((M, N), np.float32), np.empty((M, N), np.int32)
+        L.check(L.lib.dgs_spmm_csr_resident_host(h, N, p(B), p(C), p(E), 1, 2), "resident max")
+        ref, Eref = oracle.spmm(rowptr, col, val, B, "max", with_arg=True)
+        assert np.array_equal(C, ref) and np.array_equal(E, Eref)
+    finally:
+        L.lib.dgs_csr_free(h)
