@@ -268,7 +268,9 @@ static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
     if (chunk < min_chunk) chunk = min_chunk;
     if (chunk > 2 * kBatch) chunk = 2 * kBatch;
   }
-  if (chunk > 8192) chunk = 8192;
+  int cap = option(OPT_SPMM_CHUNK_CAP);
+  if (cap < 64) cap = 8192;
+  if (chunk > cap) chunk = cap;
   const size_t per_chunk = (size_t)2 * N * 4 * (with_arg ? 2 : 1) + 4;
   const int64_t min_for_ws = (int64_t)(((size_t)nnz * per_chunk + kWorkspaceCap - 1) / kWorkspaceCap);
   if (chunk < min_for_ws) chunk = min_for_ws;
