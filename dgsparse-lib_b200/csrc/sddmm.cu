@@ -461,6 +461,7 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
       int64_t chunk = (p.nnz + resident_warps * 6 - 1) / (resident_warps * 6);
       if (chunk < 64) chunk = 64;
       if (chunk > 8192) chunk = 8192;
+      if (option(OPT_SDDMM_CHUNK) >= 32) chunk = option(OPT_SDDMM_CHUNK);
       a.chunk = (int)((chunk + 31) / 32 * 32);
       a.num_chunks = (int)((p.nnz + a.chunk - 1) / a.chunk);
       const int grid = (a.num_chunks + wpc - 1) / wpc;

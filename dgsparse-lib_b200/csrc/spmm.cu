@@ -245,11 +245,14 @@ static constexpr size_t kWorkspaceCap = 192u << 20;
 // cut by a segment boundary (those are finished by the fix-up kernel, which on N GPUs is an NVLink-ingress burst).
 // Measured on B200 (option spmm_segs): the main kernel does not care (reddit@64 1.573 / 1.568 / 1.567 / 1.570 / 1.575 ms
 // for 8 / 4 / 3 / 2 / 1, products@128 8.95 / 8.93 / 8.95 ms for 8 / 4 / 3) while the fix-up shrinks with the segment count.
-// 2 everywhere — the SAME layout whether the epilogue stores locally or fans out to other GPUs, so that the column-sharded
-// result stays bit-identical to the single-GPU one (rows are folded at the same places).
+// Round 2 sweep on reddit@64 (segments per group / longest segment: step, kernel, fix-up ms): 3 / 8192: 1.580, 1.560, 0.0128;
+// 2 / 8192: 1.580, 1.563, 0.0108; 1 / 16384: 1.584, 1.569, 0.0087; 1 / 32768: 1.581, 1.566, 0.0087 — level within noise.
+// ONE segment per resident group, up to 16384 nonzeros, everywhere — the SAME layout whether the epilogue stores locally or
+// fans out to other GPUs, so that the column-sharded result stays bit-identical to the single-GPU one (rows are folded at
+// the same places) while as few rows as possible go through the fix-up grid's burst over NVLink.
 static int segs_per_group() {
   const int v = option(OPT_SPMM_SEGS);
-  return (v >= 1 && v <= 64) ? v : 2;
+  return (v >= 1 && v <= 64) ? v : 1;
 }
 
 static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
@@ -269,7 +272,7 @@ static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
     if (chunk > 2 * kBatch) chunk = 2 * kBatch;
   }
   int cap = option(OPT_SPMM_CHUNK_CAP);
-  if (cap < 64) cap = 8192;
+  if (cap < 64) cap = 16384;
   if (chunk > cap) chunk = cap;
   const size_t per_chunk = (size_t)2 * N * 4 * (with_arg ? 2 : 1) + 4;
   const int64_t min_for_ws = (int64_t)(((size_t)nnz * per_chunk + kWorkspaceCap - 1) / kWorkspaceCap);
