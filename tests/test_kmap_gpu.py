@@ -1,7 +1,8 @@
 """GPU: kernel-map construction (dgs_kmap_*) against a plain-Python / numpy restatement of the reference's query rules
 (_queryhash_subm / _queryhash_sp with padding 0, include/cuda/sparse_mapping.cuh:68-229; coordsDownsample + sort + unique,
 src/cuda/sparse_mapping.cu:68-97).  Integer work: every output must be bit-exact.  The reference has no test or fixture
-for this step (parity unpinned); the end-to-end check below runs the maps through spconv against a dense convolution."""
+for this step; the comparison with the reference's OWN sparse_mapping CUDA (compiled unmodified) lives in
+tests/test_vs_reference_spconv_gpu.py, and the end-to-end check below runs the maps through spconv against a dense convolution."""
 import numpy as np
 import pytest
 import torch
@@ -172,3 +173,29 @@ def test_maps_drive_spconv_like_a_dense_convolution():
         oc = km.out_coords.long()
         want = ref[0][:, oc[:, 1], oc[:, 2], oc[:, 3]].T
         assert torch.allclose(out.double(), want, rtol=1e-5, atol=1e-5), (ks, st)
+
+
+def test_out_of_range_coordinates_are_rejected():
+    """a voxel key holds 16 bits per component; coordinates outside (-32768, 32768) or batch indices above 65535
+    used to alias other voxels silently.  The Python face raises, the C ABI poisons knnz / kpos / qkpos with -1."""
+    from dgsparse.sparse_mapping import build_kernel_map, downsample_coords
+    from dgsparse._lib import check, lib, ptr, stream_of
+    good = torch.tensor([[0, 1, 2, 3], [0, 2, 2, 3], [1, 5, 5, 5]], dtype=torch.int32, device="cuda")
+    for bad_row in ([0, 40000, 0, 0], [0, 0, -32768, 0], [70000, 1, 1, 1], [-1, 1, 1, 1]):
+        c = torch.cat([good, torch.tensor([bad_row], dtype=torch.int32, device="cuda")])
+        with pytest.raises(ValueError):
+            build_kernel_map(c, 3, 1)
+        with pytest.raises(ValueError):
+            downsample_coords(c, 2)
+        n, k_vol = c.size(0), 27
+        imap = torch.empty(k_vol * n, dtype=torch.int32, device="cuda")
+        omap = torch.empty_like(imap)
+        knnz = torch.zeros(k_vol, dtype=torch.int32, device="cuda")
+        kpos = torch.zeros(k_vol + 1, dtype=torch.int32, device="cuda")
+        qkpos = torch.zeros(k_vol + 1, dtype=torch.int32, device="cuda")
+        ws = torch.empty(lib.dgs_kmap_workspace_bytes(n, n, k_vol), dtype=torch.uint8, device="cuda")
+        check(lib.dgs_kmap_build_ex(n, ptr(c), n, ptr(c), 3, 3, 3, 1, 1, 1, 0, 0, 0, 1, 128, 0, ptr(imap), ptr(omap), ptr(knnz),
+                                    ptr(kpos), ptr(qkpos), ptr(ws), ws.numel(), stream_of(c)), "dgs_kmap_build_ex")
+        assert int(kpos[-1]) == -1 and int(qkpos[-1]) == -1 and bool((knnz == -1).all())
+    km = build_kernel_map(good, 3, 1)          # the in-range part alone is fine
+    assert km.sum_nnz >= 0 and int(km.kpos[-1]) >= good.size(0)

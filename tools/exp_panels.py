@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Experiment (GPU): SpMM time against the column-panel width (DGS_SPMM_PANEL) on the products-like and reddit-like
-matrices.   python tools/exp_panels.py [products|reddit] [N] [--once PANEL]   (--once: a single call, for ncu)"""
+"""Experiment (GPU, round 2 — its 8 / 16-column kernels now live under tools/dead_ends/, so only widths 64 and 32 still run
+from this tree; the recorded results are profiles/r02_exp_panels_*.jsonl): SpMM time against the column-panel width
+(DGS_SPMM_PANEL, read at library load) on the products-like and reddit-like matrices.   python tools/exp_panels.py [products|reddit] [N] [--once PANEL]   (--once: a single call, for ncu)"""
 import json
 import os
 import sys
