@@ -15,6 +15,7 @@
 // U=8 edges are processed together: their D2 rows are requested back-to-back, the D1 row is shared
 // when the 8 edges lie in one CSR row, and the 8 partial dots are reduced with a transposing shuffle
 // tree (7 + log2(G/8) shuffles for 8 edges instead of 8*log2(G)); results are stored coalesced.
+#include <cstdint>
 #include <cstdlib>
 #include "common.cuh"
 #include "spmm.h"
@@ -461,6 +462,19 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
       int64_t chunk = (p.nnz + resident_warps * 6 - 1) / (resident_warps * 6);
       if (chunk < 64) chunk = 64;
       if (chunk > 8192) chunk = 8192;
+      // Latency regime (a few waves of warps at most): a warp walks its edges 4 at a time, so the call takes
+      // ceil(warps / resident warps) x chunk batches — choose the chunk that wastes no wave.  Measured on the reference's
+      // fixtures (us, chunk 64 -> chosen): p2p-Gnutella31 K=256 33.4 -> 25.6 (96), K=512 57.8 -> 54.3; ca-CondMat K=128
+      // 26.9 -> 20.9 (96), K=256 33.0 -> 31.9 (128), K=512 61.6 -> 57.5 (128); a chunk that leaves a sliver of a second wave
+      // is the worst case (ca-CondMat K=256 at 96: 43.4).
+      if (p.nnz <= resident_warps * 64 * 4) {
+        int64_t best = 64, best_cost = INT64_MAX;
+        for (int64_t c = 32; c <= 512; c += 32) {
+          const int64_t nw = (p.nnz + c - 1) / c, waves = (nw + resident_warps - 1) / resident_warps, cost = waves * c;
+          if (cost < best_cost || (cost == best_cost && c > best)) { best = c; best_cost = cost; }
+        }
+        chunk = best;
+      }
       if (option(OPT_SDDMM_CHUNK) >= 32) chunk = option(OPT_SDDMM_CHUNK);
       a.chunk = (int)((chunk + 31) / 32 * 32);
       a.num_chunks = (int)((p.nnz + a.chunk - 1) / a.chunk);

@@ -12,7 +12,7 @@
 
 namespace dgs {
 
-#define DGS_DECL_LOOKUP(V, G) SpmmLaunchFn spmm_lookup_v##V##_g##G(int red, int comp, bool arg);
+#define DGS_DECL_LOOKUP(V, G) SpmmKernel spmm_lookup_v##V##_g##G(int red, int comp, bool arg);
 DGS_DECL_LOOKUP(4, 4) DGS_DECL_LOOKUP(4, 8) DGS_DECL_LOOKUP(4, 16) DGS_DECL_LOOKUP(4, 32)
 DGS_DECL_LOOKUP(1, 4) DGS_DECL_LOOKUP(1, 8) DGS_DECL_LOOKUP(1, 16) DGS_DECL_LOOKUP(1, 32)
 SpmmLaunchFn spmm_rowpar_lookup_v4_g4(int red, int comp, bool arg);
@@ -255,8 +255,10 @@ static int segs_per_group() {
   return (v >= 1 && v <= 64) ? v : 1;
 }
 
-static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
-  const int64_t resident_groups = (int64_t)device_sm_count() * 3 * (kSpmmThreads / G);
+// blocks_per_sm: CTAs of the kernel that will run that fit on one SM (SpmmKernel::blocks_per_sm; 3 when sizing the workspace,
+// the most any flavour reaches = the most segments)
+static int pick_chunk(int N, int64_t nnz, bool with_arg, int G, int blocks_per_sm) {
+  const int64_t resident_groups = (int64_t)device_sm_count() * blocks_per_sm * (kSpmmThreads / G);
   const int spg = segs_per_group();
   int64_t chunk = (nnz + resident_groups * spg - 1) / (resident_groups * spg);
   // Small matrices (latency regime): one 32-nnz batch per segment spreads them over more SMs; with two or more column
@@ -273,7 +275,12 @@ static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
   }
   int cap = option(OPT_SPMM_CHUNK_CAP);
   if (cap < 64) cap = 16384;
-  if (chunk > cap) chunk = cap;
+  if (chunk > cap) {
+    // longer matrices: a WHOLE number of segments per resident group again — a capped segment length would leave a sliver
+    // of a second wave (products@128: 7 551 segments on 7 104 resident groups = 1.06 waves cost 9.6 ms against 8.7 ms)
+    const int64_t rounds = (nnz + resident_groups * cap - 1) / (resident_groups * cap);
+    chunk = (nnz + resident_groups * rounds - 1) / (resident_groups * rounds);
+  }
   const size_t per_chunk = (size_t)2 * N * 4 * (with_arg ? 2 : 1) + 4;
   const int64_t min_for_ws = (int64_t)(((size_t)nnz * per_chunk + kWorkspaceCap - 1) / kWorkspaceCap);
   if (chunk < min_for_ws) chunk = min_for_ws;
@@ -282,10 +289,10 @@ static int pick_chunk(int N, int64_t nnz, bool with_arg, int G) {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static void geometry_for(int N, int64_t nnz, bool with_arg, bool can_vec4, int W, int *vec, int *G, bool *narrow,
+static void geometry_for(int N, int64_t nnz, bool with_arg, bool can_vec4, int W, int blocks_per_sm, int *vec, int *G, bool *narrow,
                          int *chunk, int *num_chunks) {
   pick_geometry(N, W, can_vec4, vec, G, narrow);
-  *chunk = pick_chunk(N, nnz, with_arg, *G);
+  *chunk = pick_chunk(N, nnz, with_arg, *G, blocks_per_sm);
   *num_chunks = (int)((nnz + *chunk - 1) / *chunk);
 }
 
@@ -297,7 +304,7 @@ size_t spmm_workspace_bytes(int N, int64_t nnz, bool with_arg) {
     static const int widths[3] = {64, 32, 64};
     int vec, G, chunk, nc;
     bool narrow;
-    geometry_for(N, nnz, with_arg, pass < 2, widths[pass], &vec, &G, &narrow, &chunk, &nc);
+    geometry_for(N, nnz, with_arg, pass < 2, widths[pass], 3, &vec, &G, &narrow, &chunk, &nc);
     size_t b = align_up((size_t)nc * 4, 256) + align_up((size_t)nc * 2 * N * 4, 256) * (with_arg ? 2 : 1);
     if (b > need) need = b;
   }
@@ -363,28 +370,32 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   g_last_path = 0;
   if (p.nnz > 0) {
     const int W = pick_panel(p.N, p.K > 0 ? p.K : p.M, false);
-    geometry_for(p.N, p.nnz, with_arg, can_vec4, W, &vec, &G, &narrow, &a.chunk, &a.num_chunks);
+    pick_geometry(p.N, W, can_vec4, &vec, &G, &narrow);
+    SpmmKernel kern;
+    const int key = vec * 100 + G;
+    switch (key) {
+    case 404: kern = spmm_lookup_v4_g4(p.reduce, comp, with_arg); break;
+    case 408: kern = spmm_lookup_v4_g8(p.reduce, comp, with_arg); break;
+    case 416: kern = spmm_lookup_v4_g16(p.reduce, comp, with_arg); break;
+    case 432: kern = spmm_lookup_v4_g32(p.reduce, comp, with_arg); break;
+    case 104: kern = spmm_lookup_v1_g4(p.reduce, comp, with_arg); break;
+    case 108: kern = spmm_lookup_v1_g8(p.reduce, comp, with_arg); break;
+    case 116: kern = spmm_lookup_v1_g16(p.reduce, comp, with_arg); break;
+    case 132: kern = spmm_lookup_v1_g32(p.reduce, comp, with_arg); break;
+    }
+    if (!kern) return cudaErrorInvalidValue;
+    int bps = kern.blocks_per_sm();
+    if (bps > 3) bps = 3;      // the workspace is sized for at most 3 CTAs per SM worth of segments
+    geometry_for(p.N, p.nnz, with_arg, can_vec4, W, bps, &vec, &G, &narrow, &a.chunk, &a.num_chunks);
     const size_t tail_b = align_up((size_t)a.num_chunks * 4, 256);
     const size_t part_b = align_up((size_t)a.num_chunks * 2 * p.N * 4, 256);
     const size_t need = tail_b + part_b * (with_arg ? 2 : 1);
     if (workspace == nullptr || workspace_bytes < need) return cudaErrorInvalidValue;
-      char *w = static_cast<char *>(workspace);
+    char *w = static_cast<char *>(workspace);
     a.tail_row = reinterpret_cast<int *>(w);
     a.part_val = reinterpret_cast<float *>(w + tail_b);
     a.part_arg = with_arg ? reinterpret_cast<int *>(w + tail_b + part_b) : nullptr;
-
-    SpmmLaunchFn fn = nullptr;
-    const int key = vec * 100 + G;
-    switch (key) {
-    case 404: fn = spmm_lookup_v4_g4(p.reduce, comp, with_arg); break;
-    case 408: fn = spmm_lookup_v4_g8(p.reduce, comp, with_arg); break;
-    case 416: fn = spmm_lookup_v4_g16(p.reduce, comp, with_arg); break;
-    case 432: fn = spmm_lookup_v4_g32(p.reduce, comp, with_arg); break;
-    case 104: fn = spmm_lookup_v1_g4(p.reduce, comp, with_arg); break;
-    case 108: fn = spmm_lookup_v1_g8(p.reduce, comp, with_arg); break;
-    case 116: fn = spmm_lookup_v1_g16(p.reduce, comp, with_arg); break;
-    case 132: fn = spmm_lookup_v1_g32(p.reduce, comp, with_arg); break;
-    }
+    SpmmLaunchFn fn = kern.launch;
     if (fn == nullptr) return cudaErrorInvalidValue;
     const int gpb = kSpmmThreads / G;
     dim3 grid((a.num_chunks + gpb - 1) / gpb, (p.N + G * vec - 1) / (G * vec));

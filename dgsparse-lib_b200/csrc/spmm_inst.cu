@@ -14,32 +14,32 @@ namespace dgs {
 #define DGS_CAT(a, b, c, d) DGS_CAT_(a, b, c, d)
 #define DGS_LOOKUP DGS_CAT(spmm_lookup_v, INST_VEC, _g, INST_G)
 
-template <int RED, bool ARG> static SpmmLaunchFn by_comp(int comp) {
+template <int RED, bool ARG> static SpmmKernel by_comp(int comp) {
   switch (comp) {
-  case C_MUL: return &launch_spmm_rowseg<INST_VEC, INST_G, RED, C_MUL, ARG>;
-  case C_COPY: return &launch_spmm_rowseg<INST_VEC, INST_G, RED, C_COPY, ARG>;
+  case C_MUL: return spmm_rowseg_handle<INST_VEC, INST_G, RED, C_MUL, ARG>();
+  case C_COPY: return spmm_rowseg_handle<INST_VEC, INST_G, RED, C_COPY, ARG>();
   default: break;
   }
   if (comp == C_MASK) {  // max/min backward wrt dense: SUM only, no arg output
-    if (RED == R_SUM && !ARG) return &launch_spmm_rowseg<INST_VEC, INST_G, R_SUM, C_MASK, false>;
-    return nullptr;
+    if (RED == R_SUM && !ARG) return spmm_rowseg_handle<INST_VEC, INST_G, R_SUM, C_MASK, false>();
+    return SpmmKernel();
   }
-  if (ARG) return nullptr;  // arg index only exists on the torch face (multiply / no value)
+  if (ARG) return SpmmKernel();  // arg index only exists on the torch face (multiply / no value)
   switch (comp) {
-  case C_ADD: return &launch_spmm_rowseg<INST_VEC, INST_G, RED, C_ADD, false>;
-  case C_SUB: return &launch_spmm_rowseg<INST_VEC, INST_G, RED, C_SUB, false>;
-  case C_DIV: return &launch_spmm_rowseg<INST_VEC, INST_G, RED, C_DIV, false>;
-  default: return nullptr;
+  case C_ADD: return spmm_rowseg_handle<INST_VEC, INST_G, RED, C_ADD, false>();
+  case C_SUB: return spmm_rowseg_handle<INST_VEC, INST_G, RED, C_SUB, false>();
+  case C_DIV: return spmm_rowseg_handle<INST_VEC, INST_G, RED, C_DIV, false>();
+  default: return SpmmKernel();
   }
 }
 
-SpmmLaunchFn DGS_LOOKUP(int red, int comp, bool arg) {
+SpmmKernel DGS_LOOKUP(int red, int comp, bool arg) {
   switch (red) {
   case R_SUM:
-  case R_MEAN: return arg ? nullptr : by_comp<R_SUM, false>(comp);
+  case R_MEAN: return arg ? SpmmKernel() : by_comp<R_SUM, false>(comp);
   case R_MAX: return arg ? by_comp<R_MAX, true>(comp) : by_comp<R_MAX, false>(comp);
   case R_MIN: return arg ? by_comp<R_MIN, true>(comp) : by_comp<R_MIN, false>(comp);
-  default: return nullptr;
+  default: return SpmmKernel();
   }
 }
 

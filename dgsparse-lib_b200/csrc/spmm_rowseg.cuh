@@ -378,14 +378,46 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
   }
 }
 
-// host-side launcher of one (VEC, G, RED, COMP, ARG) instance; defined in spmm_inst_*.cu
+// host-side handle of one (VEC, G, RED, COMP, ARG) instance (instantiated in spmm_inst.cu): its launcher and how many of its
+// CTAs fit on one SM (the register count differs between flavours: 79 - 80 registers = 3 CTAs for sum / max / min, 100 - 128 =
+// 2 for the arg-tracking and masked kernels and for the 4-lane geometry).  The dispatcher sizes the segments from it so
+// that the grid is a whole number of waves.
 using SpmmLaunchFn = cudaError_t (*)(const SpmmArgs &, dim3 grid, cudaStream_t);
+struct SpmmKernel {
+  SpmmLaunchFn launch = nullptr;
+  int (*blocks_per_sm)() = nullptr;
+  explicit operator bool() const { return launch != nullptr; }
+};
 
 template <int VEC, int G, int RED, int COMP, bool ARG>
 cudaError_t launch_spmm_rowseg(const SpmmArgs &a, dim3 grid, cudaStream_t s) {
   constexpr int U = (VEC == 4) ? 8 : 8;
   spmm_rowseg_kernel<VEC, G, RED, COMP, ARG, U><<<grid, kSpmmThreads, 0, s>>>(a);
   return cudaGetLastError();
+}
+
+template <int VEC, int G, int RED, int COMP, bool ARG>
+int occupancy_spmm_rowseg() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 2;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmm_rowseg_kernel<VEC, G, RED, COMP, ARG, 8>, kSpmmThreads, 0) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = 2;
+    }
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+template <int VEC, int G, int RED, int COMP, bool ARG>
+SpmmKernel spmm_rowseg_handle() {
+  SpmmKernel k;
+  k.launch = &launch_spmm_rowseg<VEC, G, RED, COMP, ARG>;
+  k.blocks_per_sm = &occupancy_spmm_rowseg<VEC, G, RED, COMP, ARG>;
+  return k;
 }
 
 }  // namespace dgs
