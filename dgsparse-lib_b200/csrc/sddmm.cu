@@ -459,9 +459,12 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
     if (wpc >= 1) {
       g.wpc = wpc;
       const int64_t resident_warps = (int64_t)device_sm_count() * wpc;
+      // Edges per warp: the grid should be a WHOLE number of waves of resident warps (one CTA of wpc warps per SM).  Large
+      // inputs: ~6 warps per resident warp for dynamic balance, the chunk rounded up to whole 4-edge batches so that the
+      // warps fill 6 waves (arxiv@256: 128-edge chunks gave 5.13 waves = 6 at 86 %).
       int64_t chunk = (p.nnz + resident_warps * 6 - 1) / (resident_warps * 6);
-      if (chunk < 64) chunk = 64;
       if (chunk > 8192) chunk = 8192;
+      chunk = (chunk + kRgNB - 1) / kRgNB * kRgNB;
       // Latency regime (a few waves of warps at most): a warp walks its edges 4 at a time, so the call takes
       // ceil(warps / resident warps) x chunk batches — choose the chunk that wastes no wave.  Measured on the reference's
       // fixtures (us, chunk 64 -> chosen): p2p-Gnutella31 K=256 33.4 -> 25.6 (96), K=512 57.8 -> 54.3; ca-CondMat K=128
@@ -476,7 +479,7 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
         chunk = best;
       }
       if (option(OPT_SDDMM_CHUNK) >= 32) chunk = option(OPT_SDDMM_CHUNK);
-      a.chunk = (int)((chunk + 31) / 32 * 32);
+      a.chunk = (int)chunk;
       a.num_chunks = (int)((p.nnz + a.chunk - 1) / a.chunk);
       const int grid = (a.num_chunks + wpc - 1) / wpc;
       const size_t smem = (size_t)wpc * g.warp_bytes;
