@@ -351,12 +351,14 @@ def secondary_run(name, args, dev, hbm_peak):
         step()
     e1.record()
     torch.cuda.synchronize()
-    ids, ms = (ctypes.c_int * 64)(), (ctypes.c_float * 64)()
-    nrec = L.lib.dgs_profile_collect(64, ids, ms)
+    ids, ms = (ctypes.c_int * 4096)(), (ctypes.c_float * 4096)()
+    nrec = L.lib.dgs_profile_collect(4096, ids, ms)
     L.lib.dgs_profile_enable(0)
-    kern = [ms[i] for i in range(nrec) if ids[i] == main_id]
+    # a step may be several launches of the kernel family (column-slab passes: one per slab, plus the partition, id 7)
+    kern = [ms[i] for i in range(nrec) if ids[i] in (main_id, 7)]
     step_ms = e0.elapsed_time(e1) / steps
-    k_avg = sum(kern) / len(kern) if kern else step_ms
+    k_avg = sum(kern) / steps if kern else step_ms
+    launches = nrec // steps if nrec else None
     if wl["op"] == "sddmm_csr":
         e = np.unique(np.concatenate([np.linspace(0, nnz - 1, 256).astype(np.int64)]))
         rows = np.searchsorted(rowptr, e, side="right") - 1
@@ -368,9 +370,12 @@ def secondary_run(name, args, dev, hbm_peak):
     traffic, tnote = ncu_traffic(name)
     res = {"workload": f"{wl['op']} on {wl['name']}, M=K={M}, nnz={nnz}, feat={N}, fp32", "steps": steps, "warmup": warm,
            "ms_per_step": step_ms, "value": flop / (step_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "parity_ok": ok,
+           "profiled_scopes_per_step": launches,
            "roofline": {"bound": "hbm", "achieved": alg_bytes / (k_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / (k_avg * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "traffic_source": tnote,
-                        "kernel_ms_avg": k_avg, "algorithmic_bytes_per_launch": alg_bytes}}
+                        "kernel_ms_avg": k_avg, "algorithmic_bytes_per_launch": alg_bytes,
+                        "note": "kernel_ms_avg = all launches of the SpMM / SDDMM kernel family in one step (a column-slab SpMM "
+                                "is one partition + one kernel per slab); achieved = algorithmic bytes of the step / that"}}
     if not args.no_ref_cuda:
         res["reference_cuda"] = reference_cuda_run(wl, M, N, nnz, rp, cc, vv, B, D1, D2, step, steps, warm, flop)
     return res
@@ -477,12 +482,12 @@ def main():
     e1.record()
     barrier()
     total_ms = e0.elapsed_time(e1)
-    ids = (ctypes.c_int * (4 * args.steps + 8))()
-    ms = (ctypes.c_float * (4 * args.steps + 8))()
+    ids = (ctypes.c_int * (64 * args.steps + 8))()
+    ms = (ctypes.c_float * (64 * args.steps + 8))()
     nrec = L.lib.dgs_profile_collect(len(ids), ids, ms)
     L.lib.dgs_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
-    kern_ms = [ms[i] for i in range(nrec) if ids[i] == main_id]
+    kern_ms = [ms[i] for i in range(nrec) if ids[i] in (main_id, 7)]     # 7 = the column-slab partition (products-like operands)
     fix_ms = [ms[i] for i in range(nrec) if ids[i] == 2]
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -651,7 +656,7 @@ def main():
 
     if rank == 0:
         traffic, traffic_note = ncu_traffic(args.workload)
-        k_avg = sum(kern_ms) / max(1, len(kern_ms)) if kern_ms else ms_per_step
+        k_avg = sum(kern_ms) / args.steps if kern_ms else ms_per_step     # all launches of the kernel family in one step
         achieved = alg_bytes / (k_avg * 1e-3) / 1e9
         line = {
             "metric": "spmm_gflops" if wl["op"] != "sddmm_csr" else "sddmm_gflops",
@@ -667,14 +672,14 @@ def main():
                          "traffic": traffic if args.scale == 1.0 else None, "traffic_source": traffic_note,
                          "peak_source": peak_src,
                          "kernel": "spmm_rowseg_kernel" if main_id == 1 else "sddmm_ring_kernel",
-                         "kernel_ms_avg": k_avg, "fixup_ms_avg": (sum(fix_ms) / len(fix_ms)) if fix_ms else None,
+                         "kernel_ms_avg": k_avg, "fixup_ms_avg": (sum(fix_ms) / args.steps) if fix_ms else None,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "gather_bytes_per_launch": 4.0 * nnz * N,
                          "l2_gather_gbs": 4.0 * nnz * N / (k_avg * 1e-3) / 1e9,
                          "note": "gathered B rows (nnz*N*4 B) are served by L2 (l2_gather_gbs; ncu: lts__throughput 83 % of "
                                  "peak on reddit@64, profiles/r01_ncu_full_reddit64.txt): that bandwidth, not HBM, bounds "
                                  "the kernel when B fits L2 — see DESIGN.md 4.1"},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": max(launches_per_step * args.steps, nrec),
             "clocks": clocks,
         }
         line.update(extra)

@@ -333,6 +333,7 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   a.mean = (p.reduce == R_MEAN);
   a.nnz_dev = p.nnz_on_device ? 1 : 0;
   a.nnz_report = p.nnz_report;
+  a.slab = p.slab_pass; a.accum = p.accum; a.rowptr_full = p.rowptr_full;
   a.n_dst = p.n_dst;
   a.mcast = p.mcast;
   if (p.mcast && p.n_dst != 1) return cudaErrorInvalidValue;
@@ -344,11 +345,15 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   a.part_val = nullptr; a.part_arg = nullptr; a.tail_row = nullptr;
   a.hub_flag = nullptr; a.hub_limit = kRowParLimit;
 
+  // dense operand far beyond the L2: column-slab passes (spmm_slab.cu) when the caller's workspace holds the partition
+  if (spmm_slab_eligible(p, can_vec4, comp, workspace_bytes) && workspace != nullptr)
+    return spmm_csr_slabbed(p, workspace, workspace_bytes, stream);
+
   // latency regime: single-launch row-parallel kernel when this matrix is known to have short rows only
   int note = -1;
   bool want_scan = false;
   const int rp_mode = rowpar_mode();
-  if (p.nnz > 0 && p.nnz <= kRowParMaxNnz && can_vec4 && (comp == C_MUL || comp == C_COPY) && rp_mode != 0) {
+  if (p.nnz > 0 && p.nnz <= kRowParMaxNnz && can_vec4 && (comp == C_MUL || comp == C_COPY) && rp_mode != 0 && !p.slab_pass) {
     int verdict = -1, *flag_dev = nullptr;
     note = note_lookup(p.rowptr, p.M, &verdict, &flag_dev, &want_scan);
     if (note >= 0) a.hub_flag = flag_dev;

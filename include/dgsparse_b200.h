@@ -29,6 +29,11 @@ int dgs_sm_count(void);
 /* Scratch the SpMM needs for rows cut by a segment boundary (see csrc/spmm_rowseg.cuh). */
 size_t dgs_spmm_workspace_bytes(int N, int64_t nnz, int with_arg);
 
+/* The same, knowing the matrix shape: when B (K rows) is far larger than the L2 the SpMM runs as column-slab passes over a
+ * slab-partitioned copy of A (csrc/spmm_slab.cu), which needs 8 nnz + 4 S M bytes more scratch.  dgs_spmm_csr / _k take that
+ * path exactly when the workspace they are given is this large; with dgs_spmm_workspace_bytes they keep the plain kernel. */
+size_t dgs_spmm_workspace_bytes_k(int M, int K, int N, int64_t nnz, int with_arg);
+
 /* Generalized CSR SpMM:  C[r, :] = REDUCE_{p in row r} COMPUTE(val[p], B[col[p], :]).
  * Replaces spmm_cuda(Tensor...) src/cuda/spmm_cuda.cu:14-253 (algorithm 0 semantics,
  * include/cuda/spmm_cuda.cuh:10-55) and GSpMM_cuda / GSpMM_no_value_cuda src/gspmm-fp/gspmm.cu:442-473.
