@@ -126,7 +126,7 @@ std::mutex g_note_mu;
 GraphNote g_notes[32];
 int g_note_clock = 0;
 
-thread_local int g_last_path = 0;   // 0 = row-segment kernel + fix-up, 1 = row-parallel single launch
+thread_local int g_last_path = 0;   // 0 = row-segment kernel + fix-up, 1 = row-parallel single launch, 2 = column-slab passes
 
 int rowpar_mode() {   // option spmm_rowpar: 0 = never, 1 = always (tests), unset (-1) = by graph note
   const int v = option(OPT_SPMM_ROWPAR);
@@ -346,8 +346,11 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   a.hub_flag = nullptr; a.hub_limit = kRowParLimit;
 
   // dense operand far beyond the L2: column-slab passes (spmm_slab.cu) when the caller's workspace holds the partition
-  if (spmm_slab_eligible(p, can_vec4, comp, workspace_bytes) && workspace != nullptr)
-    return spmm_csr_slabbed(p, workspace, workspace_bytes, stream);
+  if (spmm_slab_eligible(p, can_vec4, comp, workspace_bytes) && workspace != nullptr) {
+    const cudaError_t se = spmm_csr_slabbed(p, workspace, workspace_bytes, stream);
+    g_last_path = 2;
+    return se;
+  }
 
   // latency regime: single-launch row-parallel kernel when this matrix is known to have short rows only
   int note = -1;

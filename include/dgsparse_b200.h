@@ -50,7 +50,8 @@ int dgs_spmm_csr(int M, int N, int64_t nnz, const int *rowptr, const int *col, c
 int dgs_set_option(const char *name, int value);
 
 /* Which kernel family the calling thread's last SpMM launched: 0 = row-segment kernel + fix-up (two launches, any matrix),
- * 1 = row-parallel single launch (latency regime, matrices the library has seen to have short rows only). */
+ * 1 = row-parallel single launch (latency regime, matrices the library has seen to have short rows only),
+ * 2 = column-slab passes (dense operand far beyond the L2; needs the dgs_spmm_workspace_bytes_k scratch). */
 int dgs_spmm_last_path(void);
 /* Forget what the library has learnt about the matrices it has seen (which ones may take the row-parallel kernel):
  * the next call on any matrix starts from the row-segment path again.  For tests and benchmarks. */

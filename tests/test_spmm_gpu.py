@@ -481,10 +481,11 @@ def test_column_slab_passes_forced(K, oracle, graphs, knob, N, slab_rows):
     val = graphs.uniform(col.size, 1, 0.5, 1.5)
     B = graphs.uniform(Kc * N, 2, -1.0, 1.0).reshape(Kc, N)
     d = [dev(rowptr), dev(col), dev(val), dev(B)]
-    assert L.lib.dgs_spmm_workspace_bytes_k(M, Kc, N, col.size, 0) > L.lib.dgs_spmm_workspace_bytes(N, col.size, 0)
+    assert L.lib.dgs_spmm_workspace_bytes_k(M, Kc, N, col.size, 0) >= L.lib.dgs_spmm_workspace_bytes(N, col.size, 0)
     for reduce in ("sum", "mean", "max", "min"):
         for v, hv in ((d[2], val), (None, None)):
             got = K.spmm(d[0], d[1], v, d[3], RED[reduce], COMP["mul"])
+            assert L.lib.dgs_spmm_last_path() == 2             # the column-slab path really ran
             ref = oracle.spmm(rowptr, col, hv, B, reduce, "mul")
             if reduce in ("max", "min"):
                 assert np.array_equal(got.cpu().numpy(), ref), (reduce, hv is None)
@@ -493,5 +494,6 @@ def test_column_slab_passes_forced(K, oracle, graphs, knob, N, slab_rows):
                                  absref=spmm_absref(oracle, rowptr, col, hv, B, reduce))
     # with the arg index the plain kernel runs (the slab path has no arg tracking) and still answers exactly
     out, E = K.spmm(d[0], d[1], d[2], d[3], RED["max"], COMP["mul"], with_arg=True)
+    assert L.lib.dgs_spmm_last_path() != 2
     ref, Eref = oracle.spmm(rowptr, col, val, B, "max", "mul", with_arg=True)
     assert np.array_equal(out.cpu().numpy(), ref) and np.array_equal(E.cpu().numpy(), Eref)
