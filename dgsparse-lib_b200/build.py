@@ -28,7 +28,7 @@ GEOMS = [(4, 4), (4, 8), (4, 16), (4, 32), (1, 4), (1, 8), (1, 16), (1, 32)]
 
 def units():
     u = []
-    for name in ["spmm.cu", "spmm_slab.cu", "sddmm.cu", "csr2csc.cu", "cabi.cu", "spconv.cu", "kmap.cu", "options.cu"]:
+    for name in ["spmm.cu", "sddmm.cu", "csr2csc.cu", "cabi.cu", "spconv.cu", "kmap.cu", "options.cu"]:
         if os.path.exists(os.path.join(CSRC, name)):
             u.append((name, [], name.replace(".cu", ".o")))
     for v, g in GEOMS:

@@ -184,15 +184,6 @@ size_t dgs_spmm_workspace_bytes(int N, int64_t nnz, int with_arg) {
   return dgs::spmm_workspace_bytes(N, nnz, with_arg != 0);
 }
 
-size_t dgs_spmm_workspace_bytes_k(int M, int K, int N, int64_t nnz, int with_arg) {
-  size_t need = dgs::spmm_workspace_bytes(N, nnz, with_arg != 0);
-  if (!with_arg) {
-    const size_t slab = dgs::spmm_slab_workspace_bytes(M, K, N, nnz);
-    if (slab > need && dgs::spmm_slab_wanted(M, K, N, nnz)) need = slab;
-  }
-  return need;
-}
-
 int dgs_spmm_csr_multi(int M, int N, int64_t nnz, const int *rowptr, const int *col, const float *val, const float *B,
                        int64_t ldb, int n_dst, float *const *dst, int64_t ldc, int reduce, int compute, void *workspace,
                        size_t workspace_bytes, void *stream) {

@@ -121,10 +121,6 @@ static cudaError_t exclusive_scan_inplace(int *a, int64_t n, int *scratch, cudaS
   return cudaGetLastError();
 }
 
-// the same scan for other translation units (spmm_slab.cu)
-size_t exclusive_scan_scratch_ints(int64_t n) { return scan_scratch_ints(n); }
-cudaError_t exclusive_scan_i32(int *a, int64_t n, int *scratch, cudaStream_t s) { return exclusive_scan_inplace(a, n, scratch, s); }
-
 // ---- row index of every nnz position ------------------------------------------------------------
 __global__ void __launch_bounds__(256) expand_rows(const int *__restrict__ rowptr, int M, int *__restrict__ row) {
   const int lane = threadIdx.x & 31;

@@ -7,9 +7,9 @@
 
 namespace dgs {
 namespace {
-const char *kNames[OPT_COUNT] = {"spmm_rowpar", "spmm_panel", "spmm_no_pdl", "spmm_segs", "spmm_chunk_cap", "spmm_slab", "spmm_slab_rows", "sddmm_no_ring", "sddmm_stages",
+const char *kNames[OPT_COUNT] = {"spmm_rowpar", "spmm_panel", "spmm_no_pdl", "spmm_segs", "spmm_chunk_cap", "sddmm_no_ring", "sddmm_stages",
                                  "sddmm_chunk"};
-const char *kEnv[OPT_COUNT] = {"DGS_SPMM_ROWPAR", "DGS_SPMM_PANEL", "DGS_SPMM_NO_PDL", "DGS_SPMM_SEGS", "DGS_SPMM_CHUNK_CAP", "DGS_SPMM_SLAB", "DGS_SPMM_SLAB_ROWS", "DGS_SDDMM_NO_RING",
+const char *kEnv[OPT_COUNT] = {"DGS_SPMM_ROWPAR", "DGS_SPMM_PANEL", "DGS_SPMM_NO_PDL", "DGS_SPMM_SEGS", "DGS_SPMM_CHUNK_CAP", "DGS_SDDMM_NO_RING",
                                "DGS_SDDMM_STAGES", "DGS_SDDMM_CHUNK"};
 std::atomic<int> g_env[OPT_COUNT];
 std::atomic<int> g_override[OPT_COUNT];

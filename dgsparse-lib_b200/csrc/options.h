@@ -6,15 +6,13 @@
 //   spmm_no_pdl      DGS_SPMM_NO_PDL           1: fix-up grid not launched as a programmatic dependent
 //   spmm_segs        DGS_SPMM_SEGS             segments per resident lane group
 //   spmm_chunk_cap   DGS_SPMM_CHUNK_CAP        longest segment (nonzeros)
-//   spmm_slab        DGS_SPMM_SLAB             0 never / 1 always (where the kernels allow) take the column-slab SpMM
-//   spmm_slab_rows   DGS_SPMM_SLAB_ROWS        rows of B per column slab (default: 0.45 L2 / 256 B)
 //   sddmm_no_ring    DGS_SDDMM_NO_RING         1: register-staged SDDMM kernel for every K
 //   sddmm_stages     DGS_SDDMM_STAGES          2 | 3 ring stages
 //   sddmm_chunk      DGS_SDDMM_CHUNK           edges per warp of the ring kernel (multiple of 32)
 #pragma once
 
 namespace dgs {
-enum Option { OPT_SPMM_ROWPAR = 0, OPT_SPMM_PANEL, OPT_SPMM_NO_PDL, OPT_SPMM_SEGS, OPT_SPMM_CHUNK_CAP, OPT_SPMM_SLAB, OPT_SPMM_SLAB_ROWS, OPT_SDDMM_NO_RING, OPT_SDDMM_STAGES, OPT_SDDMM_CHUNK, OPT_COUNT };
+enum Option { OPT_SPMM_ROWPAR = 0, OPT_SPMM_PANEL, OPT_SPMM_NO_PDL, OPT_SPMM_SEGS, OPT_SPMM_CHUNK_CAP, OPT_SDDMM_NO_RING, OPT_SDDMM_STAGES, OPT_SDDMM_CHUNK, OPT_COUNT };
 int option(Option o);                          // -1 when unset
 int set_option(const char *name, int value);   // value < 0 clears the override (back to the environment); 0 ok, -1 unknown name
 }  // namespace dgs

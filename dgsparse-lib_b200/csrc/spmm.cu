@@ -126,7 +126,7 @@ std::mutex g_note_mu;
 GraphNote g_notes[32];
 int g_note_clock = 0;
 
-thread_local int g_last_path = 0;   // 0 = row-segment kernel + fix-up, 1 = row-parallel single launch, 2 = column-slab passes
+thread_local int g_last_path = 0;   // 0 = row-segment kernel + fix-up, 1 = row-parallel single launch
 
 int rowpar_mode() {   // option spmm_rowpar: 0 = never, 1 = always (tests), unset (-1) = by graph note
   const int v = option(OPT_SPMM_ROWPAR);
@@ -333,7 +333,6 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   a.mean = (p.reduce == R_MEAN);
   a.nnz_dev = p.nnz_on_device ? 1 : 0;
   a.nnz_report = p.nnz_report;
-  a.slab = p.slab_pass; a.accum = p.accum; a.rowptr_full = p.rowptr_full;
   a.n_dst = p.n_dst;
   a.mcast = p.mcast;
   if (p.mcast && p.n_dst != 1) return cudaErrorInvalidValue;
@@ -345,18 +344,11 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   a.part_val = nullptr; a.part_arg = nullptr; a.tail_row = nullptr;
   a.hub_flag = nullptr; a.hub_limit = kRowParLimit;
 
-  // dense operand far beyond the L2: column-slab passes (spmm_slab.cu) when the caller's workspace holds the partition
-  if (spmm_slab_eligible(p, can_vec4, comp, workspace_bytes) && workspace != nullptr) {
-    const cudaError_t se = spmm_csr_slabbed(p, workspace, workspace_bytes, stream);
-    g_last_path = 2;
-    return se;
-  }
-
   // latency regime: single-launch row-parallel kernel when this matrix is known to have short rows only
   int note = -1;
   bool want_scan = false;
   const int rp_mode = rowpar_mode();
-  if (p.nnz > 0 && p.nnz <= kRowParMaxNnz && can_vec4 && (comp == C_MUL || comp == C_COPY) && rp_mode != 0 && !p.slab_pass) {
+  if (p.nnz > 0 && p.nnz <= kRowParMaxNnz && can_vec4 && (comp == C_MUL || comp == C_COPY) && rp_mode != 0) {
     int verdict = -1, *flag_dev = nullptr;
     note = note_lookup(p.rowptr, p.M, &verdict, &flag_dev, &want_scan);
     if (note >= 0) a.hub_flag = flag_dev;

@@ -30,17 +30,7 @@ struct SpmmProblem {
   // host memory, may be null) for the next call.  No device->host copy, no synchronisation.
   bool nnz_on_device = false;
   int *nnz_report = nullptr;
-  // Column-slab passes (spmm_slab.cu; set by spmm_csr_slabbed only): rowptr / col / val describe ONE column slab of a
-  // slab-partitioned copy of A whose nnz stream is [rowptr[0], rowptr[M]); accum: combine with what C holds.
-  int slab_pass = 0;
-  int accum = 0;
-  const int *rowptr_full = nullptr;
 };
-
-bool spmm_slab_wanted(int M, int K, int N, int64_t nnz);
-bool spmm_slab_eligible(const SpmmProblem &p, bool can_vec4, int comp, size_t workspace_bytes);
-size_t spmm_slab_workspace_bytes(int M, int K, int N, int64_t nnz);   // 0 when the slab path does not apply
-cudaError_t spmm_csr_slabbed(const SpmmProblem &p, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 
 size_t spmm_workspace_bytes(int N, int64_t nnz, bool with_arg);
 cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_bytes, cudaStream_t stream);

@@ -55,35 +55,18 @@ struct SpmmArgs {
   int *nnz_report;    // (with nnz_dev) mapped host word that receives the true nnz: the next call's hint
   int *hub_flag;      // mapped host word set to 1 when a row longer than kRowParLimit is seen (null: nobody asks)
   int hub_limit;
-  // column-slab passes (spmm_slab.cu): this launch covers the nonzeros of ONE column slab of a slab-partitioned copy of A;
-  // its nnz stream is [rowptr[0], rowptr[M]) (absolute positions, known on the device only: nnz_dev is set)
-  int slab;                // 1 in a slab pass
-  int accum;               // combine a finished row with what C already holds (every slab pass but the first)
-  const int *rowptr_full;  // row pointer of the whole matrix: which rows are empty in ALL slabs
 };
-
-template <int RED, int VEC> __device__ __forceinline__ void combine_with_prev(float (&o)[VEC], const float *prev_ptr) {
-  float pv[VEC];
-  ld_vec<VEC>(pv, prev_ptr);
-#pragma unroll
-  for (int v = 0; v < VEC; v++) {
-    if (RED == R_MAX) o[v] = (pv[v] < o[v]) ? o[v] : pv[v];
-    else if (RED == R_MIN) o[v] = (pv[v] < o[v]) ? pv[v] : o[v];
-    else o[v] = pv[v] + o[v];
-  }
-}
 
 // Segment layout actually used by a launch.  Normally the host's (a.nnz, a.chunk, a.num_chunks).  The legacy entry points
 // (spmm_cuda(m, k, rowptr, ...): no nnz argument) must not block on a device->host copy of rowptr[M], so there the host
 // sizes the grid and the workspace from the nnz it saw on the previous call with this rowptr (a hint) and every kernel
 // re-derives the layout from the true nnz: same segments when the hint was right, fewer when nnz shrank, LONGER segments
 // (never more than the a.num_chunks the workspace was sized for) when it grew.
-struct SegLayout { int nnz, chunk, num_chunks, begin; };   // the stream is [begin, begin + nnz)
+struct SegLayout { int nnz, chunk, num_chunks; };
 __device__ __forceinline__ SegLayout seg_layout(const SpmmArgs &a) {
-  SegLayout s = {a.nnz, a.chunk, a.num_chunks, 0};
+  SegLayout s = {a.nnz, a.chunk, a.num_chunks};
   if (a.nnz_dev) {
-    s.begin = a.slab ? __ldg(a.rowptr) : 0;
-    s.nnz = __ldg(a.rowptr + a.M) - s.begin;
+    s.nnz = __ldg(a.rowptr + a.M);
     const int need = (int)(((int64_t)s.nnz + a.num_chunks - 1) / a.num_chunks);
     if (need > s.chunk) s.chunk = (need + 31) / 32 * 32;
     s.num_chunks = (int)(((int64_t)s.nnz + s.chunk - 1) / s.chunk);
@@ -137,8 +120,8 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
   const SegLayout sl = seg_layout(a);
   if (chunk_id >= sl.num_chunks) return;
 
-  const int lo = sl.begin + chunk_id * sl.chunk;
-  const int hi = (sl.begin + sl.nnz - lo <= sl.chunk) ? sl.begin + sl.nnz : lo + sl.chunk;
+  const int lo = chunk_id * sl.chunk;
+  const int hi = (sl.nnz - lo <= sl.chunk) ? sl.nnz : lo + sl.chunk;
   const int colbase = blockIdx.y * (G * VEC) + gl * VEC;
   const bool active = colbase < a.N;
   // lanes beyond a ragged N recompute panel 0 (always in bounds) and never store: no predication in the hot loop
@@ -178,7 +161,6 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArg
 #pragma unroll
         for (int v = 0; v < VEC; v++) o[v] = a.mean ? acc[v] / deg : acc[v];
         const size_t off = (size_t)r * a.ldc + colbase;
-        if (a.accum) combine_with_prev<RED, VEC>(o, a.dst[0] + off);            // column-slab pass: C holds the earlier slabs
         if (a.mcast) st_vec_multimem<VEC>(a.dst[0] + off, o);                   // NVSwitch multicast: all ranks at once
         else {
           st_vec_cs<VEC>(a.dst[0] + off, o);
@@ -320,18 +302,15 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
       hub = deg > a.hub_limit;
     }
     if (a.hub_flag && __any_sync(0xffffffffu, hub) && lane == 0) *a.hub_flag = 1;   // not a matrix for the row-parallel kernel
-    unsigned m = a.accum ? 0u : __ballot_sync(0xffffffffu, empty);   // later slab passes leave rows they do not touch alone
+    unsigned m = __ballot_sync(0xffffffffu, empty);
     while (m) {
       const int rr = (int)row0 + (__ffs(m) - 1);
       m &= m - 1;
-      // first slab pass, max / min: a row that is empty HERE but not in every slab starts from the reduce identity
-      float fill = 0.0f;
-      if (a.slab && (RED == R_MAX || RED == R_MIN) && __ldg(a.rowptr_full + rr) != __ldg(a.rowptr_full + rr + 1)) fill = reduce_identity<RED>();
       for (int c = lane * FV; c < a.N; c += 32 * FV) {   // FV = 4: 16-byte stores (N % 4 == 0, aligned rows)
         float z[FV];
         int m1[FV];
 #pragma unroll
-        for (int v = 0; v < FV; v++) { z[v] = fill; m1[v] = -1; }
+        for (int v = 0; v < FV; v++) { z[v] = 0.0f; m1[v] = -1; }
         if (a.mcast) st_vec_multimem<FV>(a.dst[0] + (size_t)rr * a.ldc + c, z);
         else for (int d = 0; d < a.n_dst; d++) st_vec_cs<FV>(a.dst[d] + (size_t)rr * a.ldc + c, z);
         if (ARG) st_vec_cs<FV>(a.E + (size_t)rr * a.lde + c, m1);
@@ -351,7 +330,7 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
     const int r = a.tail_row[g];
     if (r >= 0) {
       const int start = __ldg(a.rowptr + r), end = __ldg(a.rowptr + r + 1);
-      const int g_last = (end - 1 - sl.begin) / sl.chunk;
+      const int g_last = (end - 1) / sl.chunk;
       float acc[FV];
       int arg[FV];
       ld_vec<FV>(acc, a.part_val + ((size_t)g * 2 + 1) * a.N + c);
@@ -392,7 +371,6 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const SpmmArgs a) {
         for (int v = 0; v < FV; v++) acc[v] = acc[v] / deg;
       }
       const size_t off = (size_t)r * a.ldc + c;
-      if (a.accum) combine_with_prev<RED, FV>(acc, a.dst[0] + off);
       if (a.mcast) st_vec_multimem<FV>(a.dst[0] + off, acc);
       else for (int d = 0; d < a.n_dst; d++) st_vec_cs<FV>(a.dst[d] + off, acc);
       if (ARG) st_vec_cs<FV>(a.E + (size_t)r * a.lde + c, arg);

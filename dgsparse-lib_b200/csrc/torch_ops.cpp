@@ -65,7 +65,7 @@ Tensor spmm_fwd(const Tensor &rowptr_, const Tensor &col_, const Tensor &values_
   Tensor E;
   if (E_out) E = at::empty({M, N}, dense.options().dtype(at::kInt));
   if (M > 0 && N > 0) {
-    const size_t wsb = dgs_spmm_workspace_bytes_k((int)M, (int)dense.size(0), (int)N, nnz, E_out != nullptr);
+    const size_t wsb = dgs_spmm_workspace_bytes((int)N, nnz, E_out != nullptr);
     Tensor ws = scratch(wsb, dense);
     check(dgs_spmm_csr_k((int)M, (int)dense.size(0), (int)N, nnz, iptr(rowptr), iptr(col), fptr(values), fptr(dense),
                          dense.stride(0), out.data_ptr<float>(), N, E_out ? E.data_ptr<int>() : nullptr, E_out ? N : 0, reduce,

@@ -42,7 +42,7 @@ def spmm(rowptr, col, values, dense, reduce=_lib.SUM, compute=_lib.MUL, with_arg
         E = torch.empty((M, N), dtype=torch.int32, device=dense.device) if with_arg else None
         if M == 0 or N == 0:
             return (out, E) if with_arg else out
-        ws_bytes = lib.dgs_spmm_workspace_bytes_k(M, dense.size(0), N, nnz, int(with_arg))
+        ws_bytes = lib.dgs_spmm_workspace_bytes(N, nnz, int(with_arg))
         ws = _workspace(ws_bytes, dense.device)
         check(lib.dgs_spmm_csr_k(M, dense.size(0), N, nnz, ptr(rowptr), ptr(col), ptr(values), ptr(dense), dense.stride(0),
                                  ptr(out), out.stride(0), ptr(E), N if with_arg else 0, int(reduce), int(compute),

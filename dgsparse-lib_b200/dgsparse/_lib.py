@@ -28,7 +28,6 @@ SIGNATURES = {
     "dgs_spmm_last_path": (_i32, []),
     "dgs_spmm_forget_graph_notes": (None, []),
     "dgs_set_option": (_i32, [ctypes.c_char_p, _i32]),
-    "dgs_spmm_workspace_bytes_k": (_sz, [_i32, _i32, _i32, _i64, _i32]),
     "dgs_spmm_csr_k": (_i32, [_i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _sz, _vp]),
     "dgs_spmm_csr_multi": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _sz, _vp]),
     "dgs_spmm_csr_mcast": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _sz, _vp]),

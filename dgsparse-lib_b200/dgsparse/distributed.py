@@ -72,10 +72,7 @@ class ColumnShardedSpMM:
         self.lo, self.hi = shard_columns(self.n_total, self.world)[self.rank]
         self.reduce, self.compute = reduce, compute
         dev = col.device
-        # one rank: the plain C-ABI call, with the K-aware scratch (column-slab passes when B is far beyond the L2)
-        ws_bytes = (_lib.lib.dgs_spmm_workspace_bytes_k(self.M, self.M, n_local, self.nnz, 0) if self.world == 1
-                    else _lib.lib.dgs_spmm_workspace_bytes(n_local, self.nnz, 0))
-        self.ws = torch.empty(max(256, ws_bytes), dtype=torch.uint8, device=dev)
+        self.ws = torch.empty(max(256, _lib.lib.dgs_spmm_workspace_bytes(n_local, self.nnz, 0)), dtype=torch.uint8, device=dev)
         self.C = None          # [2, M, n_total]: double-buffered output (see the module docstring), index = call parity
         self._calls = 0
         self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -172,11 +169,9 @@ class ColumnShardedSpMM:
             self.barrier(stream)                            # completion barrier: every rank's multicast stores have landed
             return self.C[buf]
         if self.mode == "local":
-            L.check(lib.dgs_spmm_csr_k(self.M, B_local.size(0), self.n_local, self.nnz, ptr(self.rowptr), ptr(self.col), ptr(self.values),
-                                       ptr(B_local), B_local.stride(0), self.C.data_ptr(), self.n_total, None, 0, self.reduce,
-                                       self.compute, ptr(self.ws), self.ws.numel(), stream), "dgs_spmm_csr_k")
-            return self.C[0]
-        dst = self._dst[buf]
+            dst = (ctypes.c_void_p * 1)(self.C.data_ptr())
+        else:
+            dst = self._dst[buf]
         L.check(lib.dgs_spmm_csr_multi(self.M, self.n_local, self.nnz, ptr(self.rowptr), ptr(self.col), ptr(self.values),
                                        ptr(B_local), B_local.stride(0), len(dst), dst, self.n_total, self.reduce,
                                        self.compute, ptr(self.ws), self.ws.numel(), stream), "dgs_spmm_csr_multi")

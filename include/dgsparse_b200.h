@@ -29,11 +29,6 @@ int dgs_sm_count(void);
 /* Scratch the SpMM needs for rows cut by a segment boundary (see csrc/spmm_rowseg.cuh). */
 size_t dgs_spmm_workspace_bytes(int N, int64_t nnz, int with_arg);
 
-/* The same, knowing the matrix shape: when B (K rows) is far larger than the L2 the SpMM runs as column-slab passes over a
- * slab-partitioned copy of A (csrc/spmm_slab.cu), which needs 8 nnz + 4 S M bytes more scratch.  dgs_spmm_csr / _k take that
- * path exactly when the workspace they are given is this large; with dgs_spmm_workspace_bytes they keep the plain kernel. */
-size_t dgs_spmm_workspace_bytes_k(int M, int K, int N, int64_t nnz, int with_arg);
-
 /* Generalized CSR SpMM:  C[r, :] = REDUCE_{p in row r} COMPUTE(val[p], B[col[p], :]).
  * Replaces spmm_cuda(Tensor...) src/cuda/spmm_cuda.cu:14-253 (algorithm 0 semantics,
  * include/cuda/spmm_cuda.cuh:10-55) and GSpMM_cuda / GSpMM_no_value_cuda src/gspmm-fp/gspmm.cu:442-473.
@@ -50,8 +45,7 @@ int dgs_spmm_csr(int M, int N, int64_t nnz, const int *rowptr, const int *col, c
 int dgs_set_option(const char *name, int value);
 
 /* Which kernel family the calling thread's last SpMM launched: 0 = row-segment kernel + fix-up (two launches, any matrix),
- * 1 = row-parallel single launch (latency regime, matrices the library has seen to have short rows only),
- * 2 = column-slab passes (dense operand far beyond the L2; needs the dgs_spmm_workspace_bytes_k scratch). */
+ * 1 = row-parallel single launch (latency regime, matrices the library has seen to have short rows only). */
 int dgs_spmm_last_path(void);
 /* Forget what the library has learnt about the matrices it has seen (which ones may take the row-parallel kernel):
  * the next call on any matrix starts from the row-segment path again.  For tests and benchmarks. */

@@ -465,35 +465,3 @@ def test_resident_csr_host_entry(oracle, graphs):
     finally:
         L.lib.dgs_csr_free(h)
 
-
-@pytest.mark.parametrize("N", [64, 100, 128, 256])
-@pytest.mark.parametrize("slab_rows", [256, 1024])
-def test_column_slab_passes_forced(K, oracle, graphs, knob, N, slab_rows):
-    """spmm_slab.cu — the path for dense operands far beyond the L2 — forced on a small matrix (option spmm_slab = 1, slabs of
-    256 / 1024 rows of B -> 14 / 4 slabs): A is re-partitioned by column range and every slab is one pass of the row-segment
-    kernel that combines with what C holds.  sum / mean / max / min, with and without edge values, empty rows, rows that
-    live in a single slab, hub rows that cross every slab and many segments.  max / min bit-exact, sum / mean to tolerance."""
-    import dgsparse._lib as L
-    knob("spmm_slab", 1)
-    knob("spmm_slab_rows", slab_rows)
-    M, Kc = 5000, 3500
-    rowptr, col = graphs.random_csr(M, Kc, 160000, 700 + N, empty_frac=0.25, hub=2)
-    val = graphs.uniform(col.size, 1, 0.5, 1.5)
-    B = graphs.uniform(Kc * N, 2, -1.0, 1.0).reshape(Kc, N)
-    d = [dev(rowptr), dev(col), dev(val), dev(B)]
-    assert L.lib.dgs_spmm_workspace_bytes_k(M, Kc, N, col.size, 0) >= L.lib.dgs_spmm_workspace_bytes(N, col.size, 0)
-    for reduce in ("sum", "mean", "max", "min"):
-        for v, hv in ((d[2], val), (None, None)):
-            got = K.spmm(d[0], d[1], v, d[3], RED[reduce], COMP["mul"])
-            assert L.lib.dgs_spmm_last_path() == 2             # the column-slab path really ran
-            ref = oracle.spmm(rowptr, col, hv, B, reduce, "mul")
-            if reduce in ("max", "min"):
-                assert np.array_equal(got.cpu().numpy(), ref), (reduce, hv is None)
-            else:
-                assert_close_f32(got.cpu().numpy(), ref, oracle.spmm_f64(rowptr, col, hv, B, reduce), what=f"slab N={N} {reduce}",
-                                 absref=spmm_absref(oracle, rowptr, col, hv, B, reduce))
-    # with the arg index the plain kernel runs (the slab path has no arg tracking) and still answers exactly
-    out, E = K.spmm(d[0], d[1], d[2], d[3], RED["max"], COMP["mul"], with_arg=True)
-    assert L.lib.dgs_spmm_last_path() != 2
-    ref, Eref = oracle.spmm(rowptr, col, val, B, "max", "mul", with_arg=True)
-    assert np.array_equal(out.cpu().numpy(), ref) and np.array_equal(E.cpu().numpy(), Eref)
