@@ -98,8 +98,11 @@ __device__ __forceinline__ void reduce_step(float (&acc)[VEC], int (&arg)[VEC], 
 // 64-bit broadcasts, and every row stays 16-byte aligned.
 constexpr int kStageStride = kBatch + 2;
 
+// Register budget: the sum / max / min flavours compile to 79 - 80 registers (3 CTAs per SM); left alone, ptxas gives the
+// arg-tracking flavours of the main (16-lane) geometry 100, i.e. 2 CTAs per SM, although they fit 80 with 16 - 32 bytes of
+// spill.  Ask for 3 CTAs per SM there (the masked flavour would spill 200 bytes and stays at 2).
 template <int VEC, int G, int RED, int COMP, bool ARG, int U>
-__global__ void __launch_bounds__(kSpmmThreads) spmm_rowseg_kernel(const SpmmArgs a) {
+__global__ void __launch_bounds__(kSpmmThreads, (VEC == 4 && G == 16 && COMP != C_MASK) ? 3 : 1) spmm_rowseg_kernel(const SpmmArgs a) {
   constexpr int GPB = kSpmmThreads / G;  // groups (segments) per block
   constexpr int PER = kBatch / G;        // staged entries per lane per batch
   constexpr bool HAS_VAL = (COMP != C_COPY);
