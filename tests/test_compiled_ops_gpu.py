@@ -7,7 +7,6 @@ import sys
 
 import numpy as np
 import pytest
-import torch
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

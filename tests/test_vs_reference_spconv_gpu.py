@@ -94,7 +94,6 @@ def test_kmap_strided_same_as_reference(REF, ks, stride, pad):
     if stride == 1:
         # reference: l_stride == 1 takes coordsDownsample with stride 1 (out = sorted unique in) and then queries with
         # `_queryhash_sp`; ours: the same output voxels handed to the strided query of dgs_kmap_build_ex
-        from dgsparse.sparse_mapping import KernelMap  # noqa: F401
         import dgsparse.sparse_mapping as SM
         km = _build_sp(SM, dev(in_c), dev(np.unique(in_c, axis=0)), ks, stride, pad)
     else:
