@@ -456,9 +456,17 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
     g.warp_bytes = (g.warp_bytes + 127u) & ~127u;
     int wpc = (int)((200u * 1024u) / g.warp_bytes);
     if (wpc > 16) wpc = 16;
+    // rows of <= 512 B: two CTAs of 11 warps fit one SM (90 registers x 704 threads, 2 x 11 rings <= 220 KB) = 22 resident
+    // warps instead of 16
+    int ctas_per_sm = 1;
+    if (2u * 11u * g.warp_bytes <= 220u * 1024u && option(OPT_SDDMM_WPC) != 16) { wpc = 11; ctas_per_sm = 2; }
+    if (option(OPT_SDDMM_WPC) >= 1 && option(OPT_SDDMM_WPC) <= 16 && (size_t)option(OPT_SDDMM_WPC) * g.warp_bytes <= 220u * 1024u) {
+      wpc = option(OPT_SDDMM_WPC);
+      ctas_per_sm = (2 * wpc * 32 * 90 <= 65536 && 2u * wpc * g.warp_bytes <= 220u * 1024u) ? 2 : 1;
+    }
     if (wpc >= 1) {
       g.wpc = wpc;
-      const int64_t resident_warps = (int64_t)device_sm_count() * wpc;
+      const int64_t resident_warps = (int64_t)device_sm_count() * wpc * ctas_per_sm;
       // Edges per warp: the grid should be a WHOLE number of waves of resident warps (one CTA of wpc warps per SM).  Large
       // inputs: ~6 warps per resident warp for dynamic balance, the chunk rounded up to whole 4-edge batches so that the
       // warps fill 6 waves (arxiv@256: 128-edge chunks gave 5.13 waves = 6 at 86 %).
