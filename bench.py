@@ -676,8 +676,8 @@ def main():
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "gather_bytes_per_launch": 4.0 * nnz * N,
                          "l2_gather_gbs": 4.0 * nnz * N / (k_avg * 1e-3) / 1e9,
-                         "note": "gathered B rows (nnz*N*4 B) are served by L2 (l2_gather_gbs; ncu: lts__throughput 83 % of "
-                                 "peak on reddit@64, profiles/r01_ncu_full_reddit64.txt): that bandwidth, not HBM, bounds "
+                         "note": "gathered B rows (nnz*N*4 B) are served by L2 (l2_gather_gbs; ncu: lts__lts2xbar_cycles_active 83 % of "
+                                 "peak on reddit@64, profiles/r02_ncu_full_reddit64.txt): the L2 slices' output, not HBM, bounds "
                                  "the kernel when B fits L2 — see DESIGN.md 4.1"},
             "gpu_launches": max(launches_per_step * args.steps, nrec),
             "clocks": clocks,
