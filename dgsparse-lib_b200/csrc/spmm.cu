@@ -250,16 +250,21 @@ static constexpr size_t kWorkspaceCap = 192u << 20;
 // ONE segment per resident group, up to 16384 nonzeros, everywhere — the SAME layout whether the epilogue stores locally or
 // fans out to other GPUs, so that the column-sharded result stays bit-identical to the single-GPU one (rows are folded at
 // the same places) while as few rows as possible go through the fix-up grid's burst over NVLink.
-static int segs_per_group() {
+// Exception, measured: more than four column panels in one launch (N > 256 on one GPU) — reddit-like N = 512: 14.28 / 13.85 /
+// 13.43 ms for 1 / 2 / 4 segments per group (N = 128 and 256: level).  The panels run one after the other and the gathered
+// panel changes at every transition; with one long wave per panel the transition is a long stretch in which two 60 MB panels
+// compete for the L2, with four short waves it is brief.
+static int segs_per_group(int panels) {
   const int v = option(OPT_SPMM_SEGS);
-  return (v >= 1 && v <= 64) ? v : 1;
+  if (v >= 1 && v <= 64) return v;
+  return panels > 4 ? 4 : 1;
 }
 
 // blocks_per_sm: CTAs of the kernel that will run that fit on one SM (SpmmKernel::blocks_per_sm; 3 when sizing the workspace,
 // the most any flavour reaches = the most segments)
 static int pick_chunk(int N, int64_t nnz, bool with_arg, int G, int blocks_per_sm) {
   const int64_t resident_groups = (int64_t)device_sm_count() * blocks_per_sm * (kSpmmThreads / G);
-  const int spg = segs_per_group();
+  const int spg = segs_per_group((N + 4 * G - 1) / (4 * G));   // 4 * G = columns per panel in the 16-byte geometries
   int64_t chunk = (nnz + resident_groups * spg - 1) / (resident_groups * spg);
   // Small matrices (latency regime): one 32-nnz batch per segment spreads them over more SMs; with two or more column
   // panels (N > 64) the extra cut rows cost more than that buys.  p2p-Gnutella31 / ca-CondMat, us per call, min 32 | 64 | 128:
