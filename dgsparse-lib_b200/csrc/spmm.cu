@@ -250,21 +250,22 @@ static constexpr size_t kWorkspaceCap = 192u << 20;
 // ONE segment per resident group, up to 16384 nonzeros, everywhere — the SAME layout whether the epilogue stores locally or
 // fans out to other GPUs, so that the column-sharded result stays bit-identical to the single-GPU one (rows are folded at
 // the same places) while as few rows as possible go through the fix-up grid's burst over NVLink.
-// Exception, measured: more than four column panels in one launch (N > 256 on one GPU) — reddit-like N = 512: 14.28 / 13.85 /
-// 13.43 ms for 1 / 2 / 4 segments per group (N = 128 and 256: level).  The panels run one after the other and the gathered
-// panel changes at every transition; with one long wave per panel the transition is a long stretch in which two 60 MB panels
-// compete for the L2, with four short waves it is brief.
-static int segs_per_group(int panels) {
+// That holds for the single-panel 16-lane geometry (N = 64: the headline and every rank of the column shard).  Elsewhere
+// four segments per group are better or level (`tools/bench_vs_ref.py`, ms, 1 vs 4): reddit-like N = 32 0.93 vs 0.86, N = 512
+// 14.28 vs 13.43, products-like N = 32 2.77 vs 2.35 — with several column panels per launch the gathered panel changes at every
+// transition and one long wave per panel makes that a long stretch in which two 60 MB panels compete for the L2; the 8-lane
+// geometry (four row walkers per warp) has a longer tail in a single wave.
+static int segs_per_group(int G, int panels) {
   const int v = option(OPT_SPMM_SEGS);
   if (v >= 1 && v <= 64) return v;
-  return panels > 4 ? 4 : 1;
+  return (G == 16 && panels == 1) ? 1 : 4;
 }
 
 // blocks_per_sm: CTAs of the kernel that will run that fit on one SM (SpmmKernel::blocks_per_sm; 3 when sizing the workspace,
 // the most any flavour reaches = the most segments)
 static int pick_chunk(int N, int64_t nnz, bool with_arg, int G, int blocks_per_sm) {
   const int64_t resident_groups = (int64_t)device_sm_count() * blocks_per_sm * (kSpmmThreads / G);
-  const int spg = segs_per_group((N + 4 * G - 1) / (4 * G));   // 4 * G = columns per panel in the 16-byte geometries
+  const int spg = segs_per_group(G, (N + 4 * G - 1) / (4 * G));   // 4 * G = columns per panel in the 16-byte geometries
   int64_t chunk = (nnz + resident_groups * spg - 1) / (resident_groups * spg);
   // Small matrices (latency regime): one 32-nnz batch per segment spreads them over more SMs; with two or more column
   // panels (N > 64) the extra cut rows cost more than that buys.  p2p-Gnutella31 / ca-CondMat, us per call, min 32 | 64 | 128:
