@@ -98,11 +98,14 @@ __device__ __forceinline__ void reduce_step(float (&acc)[VEC], int (&arg)[VEC], 
 // 64-bit broadcasts, and every row stays 16-byte aligned.
 constexpr int kStageStride = kBatch + 2;
 
-// Register budget: the sum / max / min flavours compile to 79 - 80 registers (3 CTAs per SM); left alone, ptxas gives the
-// arg-tracking flavours of the main (16-lane) geometry 100, i.e. 2 CTAs per SM, although they fit 80 with 16 - 32 bytes of
-// spill.  Ask for 3 CTAs per SM there (the masked flavour would spill 200 bytes and stays at 2).
+// Register budget: the sum / max / min flavours of the 8- and 16-lane vec4 geometries compile to 79 - 80 registers (3 CTAs per
+// SM); left alone, ptxas gives their arg-tracking flavours 96 - 100, i.e. 2 CTAs per SM, although they fit 80 with 8 - 24 bytes
+// of spill.  Ask for 3 CTAs per SM there (the masked flavour would spill 200 bytes, the 4-lane geometry 40: both keep the
+// compiler's own choice).  The second argument must be 0 ("unspecified") and NOT 1 for the others: 1 tells ptxas the kernel
+// may take the whole register file, it then gave the 8-lane sum kernel 124 registers, and N = 32 ran 12 - 20 % slower at
+// 2 CTAs per SM (reddit-like 0.93 against 0.84 ms, products-like 2.81 against 2.31 ms; tools/exp_ab_r1.py).
 template <int VEC, int G, int RED, int COMP, bool ARG, int U>
-__global__ void __launch_bounds__(kSpmmThreads, (VEC == 4 && G == 16 && COMP != C_MASK) ? 3 : 1) spmm_rowseg_kernel(const SpmmArgs a) {
+__global__ void __launch_bounds__(kSpmmThreads, (VEC == 4 && G >= 8 && COMP != C_MASK) ? 3 : 0) spmm_rowseg_kernel(const SpmmArgs a) {
   constexpr int GPB = kSpmmThreads / G;  // groups (segments) per block
   constexpr int PER = kBatch / G;        // staged entries per lane per batch
   constexpr bool HAS_VAL = (COMP != C_COPY);
