@@ -159,10 +159,12 @@ def test_csr2csc_shapes(K, oracle, graphs, shape):
     assert np.array_equal(perm.cpu().numpy(), ref[3])
 
 
-def test_csr2csc_full_size_above_2p24(K, graphs):
-    """reddit-like, 114.6 M nnz > 2^24 where the reference's float32-arange permutation breaks (q10).
+@pytest.mark.parametrize("graph", ["reddit_like", "products_like"])
+def test_csr2csc_full_size_above_2p24(K, graphs, graph):
+    """reddit-like (114.6 M nnz, two radix passes) and products-like (123.7 M nnz, 2.45 M columns: three passes, a suffix-minimum
+    over more than one block of tiles): > 2^24 nnz, where the reference's float32-arange permutation breaks (q10).
     Properties: perm is a permutation; col[perm] is sorted; ties keep CSR order; colptr = bincount."""
-    rowptr, col = graphs.reddit_like(1.0)
+    rowptr, col = getattr(graphs, graph)(1.0)
     M, nnz = rowptr.size - 1, col.size
     rp, cc = dev(rowptr), dev(col)
     colptr, row, _, perm = K.csr2csc(rp, cc, None, ncols=M)
