@@ -183,6 +183,14 @@ void note_scan_enqueued(int idx, const int *rowptr, cudaStream_t s) {
 }
 }  // namespace
 
+// Graph notes allocate mapped memory, record and query events: none of that belongs into a stream capture, and a captured
+// launch must not depend on what a note says at capture time.  While capturing, the segment path is taken unconditionally.
+static bool stream_is_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return true; }   // e.g. legacy stream during a global capture
+  return st != cudaStreamCaptureStatusNone;
+}
+
 int spmm_last_path() { return g_last_path; }
 void spmm_forget_graph_notes() { notes_forget(); }
 
@@ -354,7 +362,8 @@ cudaError_t spmm_csr(const SpmmProblem &p, void *workspace, size_t workspace_byt
   int note = -1;
   bool want_scan = false;
   const int rp_mode = rowpar_mode();
-  if (p.nnz > 0 && p.nnz <= kRowParMaxNnz && can_vec4 && (comp == C_MUL || comp == C_COPY) && rp_mode != 0) {
+  if (p.nnz > 0 && p.nnz <= kRowParMaxNnz && can_vec4 && (comp == C_MUL || comp == C_COPY) && rp_mode != 0 &&
+      !stream_is_capturing(stream)) {
     int verdict = -1, *flag_dev = nullptr;
     note = note_lookup(p.rowptr, p.M, &verdict, &flag_dev, &want_scan);
     if (note >= 0) a.hub_flag = flag_dev;

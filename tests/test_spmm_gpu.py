@@ -384,6 +384,33 @@ def test_row_parallel_kernel_forced(K, oracle, graphs, knob, N):
                                  what=f"rowpar N={N} {reduce}", absref=spmm_absref(oracle, rowptr, col, hv, B, reduce))
 
 
+def test_spmm_inside_cuda_graph_capture(K, oracle, graphs):
+    """The library may be captured into a CUDA graph: while a stream is capturing it must not allocate, record or query
+    anything (graph notes are skipped, the segment path is taken), and replays must follow new operand VALUES."""
+    import dgsparse._lib as L
+    rowptr, col, (M, Kc) = graphs.load_fixture("p2p-Gnutella31")
+    N = 32
+    val = graphs.uniform(col.size, 1)
+    rp, cc, vv = dev(rowptr), dev(col), dev(val)
+    L.lib.dgs_spmm_forget_graph_notes()
+    B0 = graphs.uniform(Kc * N, 2).reshape(Kc, N)
+    dB = dev(B0)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):                      # warm-up outside the capture (lazy module load), as torch asks
+        K.spmm(rp, cc, vv, dB)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = K.spmm(rp, cc, vv, dB)
+        assert L.lib.dgs_spmm_last_path() == 0        # never the note-driven kernel inside a capture
+    for seed in (2, 7):
+        Bn = graphs.uniform(Kc * N, seed).reshape(Kc, N)
+        dB.copy_(torch.from_numpy(Bn))
+        g.replay()
+        torch.cuda.synchronize()
+        assert_close_f32(out.cpu().numpy(), oracle.spmm(rowptr, col, val, Bn), what=f"graph replay {seed}")
+
+
 def test_row_parallel_selected_by_graph_note_and_healed(K, oracle, graphs):
     """The library learns from its own fix-up scan that a matrix has short rows only (p2p-Gnutella31: longest row 78) and
     switches later calls to the single-launch kernel; a matrix with a long row never switches; and a CSR rewritten IN PLACE
