@@ -41,7 +41,7 @@ constexpr int kMaxNT = 128;          // widest c_out tile (TMEM columns)
 struct SpconvArgs {
   const int *kpos, *qkpos, *imap, *omap;
   const float *in;     // [in_rows, ld_in]
-  const uint8_t *Wt;   // [k_vol][n_rows_pad][k_pad] in the MMA dtype, K contiguous (prep kernel)
+  const uint8_t *Wt;   // [k_vol][n_rows_pad / NT][n_atoms][NT][128 B swizzled] in the MMA dtype: shared-memory images (prep kernel)
   float *out;          // [out_rows, ld_out]
   int64_t ld_in, ld_out;
   int k_vol, c_in, c_out;     // GEMM K and N of this launch (swapped for the dX backward)
@@ -74,6 +74,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(a), "r"(parity) : "memory");
   } while (!done);
+}
+// TMA bulk copy global -> shared (cp.async.bulk, the copy engine writes shared memory and completes `bytes` on the mbarrier).
+// Used for the prepared weight panels, which are stored as the exact shared-memory image (spconv_prep_weights_kernel).
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// one thread: the panel of `atoms` atoms x NT rows x 128 B, one bulk copy per atom (<= 32 KB each)
+__device__ __forceinline__ void load_w_panel(uint32_t sW, const uint8_t *src, int atoms, int NT, uint64_t *bar) {
+  const uint32_t per_atom = (uint32_t)NT * 128u;
+  mbar_expect_tx(bar, per_atom * (uint32_t)atoms);
+  for (int at = 0; at < atoms; at++) bulk_g2s(sW + (uint32_t)at * per_atom, src + (size_t)at * per_atom, per_atom, bar);
+}
+// a wait that cannot hang the GPU: a copy that never completes (a bad address would fault, not stall) traps after ~1 s
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  const uint32_t a = smem_u32(bar);
+  for (uint32_t spins = 0;; spins++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (done) return;
+    if (spins > (1u << 24)) __trap();
+  }
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -175,7 +201,7 @@ template <int KIND>
 __global__ void __launch_bounds__(128) spconv_fgms_tc_kernel(const SpconvArgs a) {
   using KD = Kind<KIND>;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t s_bar;
+  __shared__ uint64_t s_bar, s_wbar;
   __shared__ uint32_t s_tmem;
   __shared__ int s_inrow[kTileM];
 
@@ -190,6 +216,7 @@ __global__ void __launch_bounds__(128) spconv_fgms_tc_kernel(const SpconvArgs a)
   if (warp == 0) tmem_alloc(&s_tmem, (uint32_t)a.tmem_cols);
   if (tid == 0) {
     mbar_init(&s_bar, 1);
+    mbar_init(&s_wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -198,7 +225,7 @@ __global__ void __launch_bounds__(128) spconv_fgms_tc_kernel(const SpconvArgs a)
   const uint32_t tmem = s_tmem;
   const uint32_t idesc = umma_idesc<KIND>(a.NT, a.f16);
   const int n0 = blockIdx.y * a.NT;
-  uint32_t phase = 0;
+  uint32_t phase = 0, wphase = 0;
   int resident_k = -1;
 
   const int n_tiles = a.n_map_tiles + a.n_id_tiles;
@@ -243,21 +270,18 @@ __global__ void __launch_bounds__(128) spconv_fgms_tc_kernel(const SpconvArgs a)
         }
       }
       // ---- W[k]^T rows [n0, n0 + NT), atoms [a0, a0 + ga): straight copy of the prepared K-major panel ----
-      if (!(w_resident && resident_k == k)) {
-        const int k_pad_bytes = a.n_atoms * kAtomBytes;
-        const uint8_t *wk = a.Wt + ((size_t)k * a.n_rows_pad + n0) * k_pad_bytes + (size_t)a0 * kAtomBytes;
-        const int items = a.NT * ga * 8;
-        for (int idx = tid; idx < items; idx += 128) {
-          const int c = idx & 7, at = (idx >> 3) % ga, n = idx / (8 * ga);
-          const uint4 w = __ldg(reinterpret_cast<const uint4 *>(wk + (size_t)n * k_pad_bytes + at * kAtomBytes + c * 16));
-          const uint32_t dst = sW + (uint32_t)at * (a.NT * kAtomBytes) + (uint32_t)n * kAtomBytes + (uint32_t)((c ^ (n & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
-        }
+      const bool load_w = !(w_resident && resident_k == k);
+      if (load_w) {
+        // the prepared panel IS the shared-memory image (swizzled): one TMA bulk copy per atom, issued by the thread that
+        // issues the MMAs (the MMAs that read the previous panel completed at the end of the previous group)
+        if (tid == 0)
+          load_w_panel(sW, a.Wt + (((size_t)k * gridDim.y + blockIdx.y) * a.n_atoms + a0) * ((size_t)a.NT * kAtomBytes), ga, a.NT, &s_wbar);
         resident_k = k;
       }
-      fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      fence_proxy_async_smem();   // generic-proxy smem writes (the gathered A) -> visible to the tensor core (async proxy)
       __syncthreads();
       if (tid == 0) {
+        if (load_w) { mbar_wait_bounded(&s_wbar, wphase); wphase ^= 1u; }
         tc_fence_after();
         for (int at = 0; at < ga; at++) {
           const int ch0 = (a0 + at) * KD::kElemsPerAtom;
@@ -363,7 +387,7 @@ template <int KIND, int DEPTH>
 __global__ void __launch_bounds__(kPipeThreads, 1) spconv_fgms_pipe_kernel(const SpconvArgs a) {
   using KD = Kind<KIND>;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t s_full[kPipeMaxStages], s_empty[kPipeMaxStages], s_tfull[2], s_tempty[2];
+  __shared__ uint64_t s_full[kPipeMaxStages], s_empty[kPipeMaxStages], s_tfull[2], s_tempty[2], s_wbar;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -377,6 +401,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) spconv_fgms_pipe_kernel(const
   if (tid == 0) {
     for (int s = 0; s < S; s++) { mbar_init(&s_full[s], 128); mbar_init(&s_empty[s], 1); }
     for (int t = 0; t < 2; t++) { mbar_init(&s_tfull[t], 1); mbar_init(&s_tempty[t], 128); }
+    mbar_init(&s_wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) tmem_alloc(&s_tmem, (uint32_t)(2 * a.tmem_cols));
@@ -393,6 +418,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) spconv_fgms_pipe_kernel(const
     // ================= gather =================
     const int cpr = a.n_atoms * 8;                 // 16-byte chunks per row
     int resident_k = -1;
+    uint32_t wphase = 0;      // parity of the weight-panel barrier
+    bool w_pending = false;   // a panel copy is in flight: it must have landed before the next full[] arrival
+    // full[] tells the MMA warp "this tile's A stage AND the resident W panel are in shared memory"
+    auto arrive_full = [&](int stage) {
+      if (w_pending) { mbar_wait_bounded(&s_wbar, wphase); wphase ^= 1u; w_pending = false; }
+      mbar_arrive(&s_full[stage]);
+    };
     int na = 0;   // next tile whose full[] arrival this thread still owes (its copies may still be in flight)
     TileCursor cur;
     int next_in = -1;   // imap entry of this lane's row of the NEXT tile, loaded one tile ahead
@@ -417,17 +449,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) spconv_fgms_pipe_kernel(const
         // (they read the resident W), then load W[k]^T rows [n0, n0 + NT).
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         fence_proxy_async_smem();
-        for (; na < i; na++) mbar_arrive(&s_full[na % S]);
+        for (; na < i; na++) arrive_full(na % S);
         for (int j = max(0, i - S); j < i; j++) mbar_wait(&s_empty[j % S], (uint32_t)(j / S) & 1u);
-        const int k_pad_bytes = a.n_atoms * kAtomBytes;
-        const uint8_t *wk = a.Wt + ((size_t)tile_k * a.n_rows_pad + n0) * k_pad_bytes;
-        const int items = a.NT * cpr;
-        for (int idx = tid; idx < items; idx += 128) {
-          const int c = idx & 7, at = (idx >> 3) % a.n_atoms, n = idx / cpr;
-          const uint4 w = __ldg(reinterpret_cast<const uint4 *>(wk + (size_t)n * k_pad_bytes + at * kAtomBytes + c * 16));
-          const uint32_t dst = sW + (uint32_t)at * (a.NT * kAtomBytes) + (uint32_t)n * kAtomBytes + (uint32_t)((c ^ (n & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
-        }
+        // The prepared panel IS the shared-memory image (swizzled): thread 0 hands it to the copy engine (one TMA bulk copy
+        // per atom) and everybody goes on gathering this tile; the copy is only waited for at the tile's full[] arrival.
+        if (tid == 0)
+          load_w_panel(sW, a.Wt + ((size_t)tile_k * gridDim.y + blockIdx.y) * ((size_t)a.n_atoms * a.NT * kAtomBytes), a.n_atoms, a.NT,
+                       &s_wbar);
+        w_pending = true;
         resident_k = tile_k;
       } else if (i >= S) {
         mbar_wait(&s_empty[s], (uint32_t)(i / S - 1) & 1u);   // the MMA that read this stage (tile i - S) is done
@@ -449,13 +478,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) spconv_fgms_pipe_kernel(const
       if (i - na >= DEPTH) {   // the oldest owed tile has at most DEPTH younger groups behind it: wait for it only
         asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH) : "memory");
         fence_proxy_async_smem();
-        mbar_arrive(&s_full[na % S]);
+        arrive_full(na % S);
         na++;
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     fence_proxy_async_smem();
-    for (; na < n_my; na++) mbar_arrive(&s_full[na % S]);
+    for (; na < n_my; na++) arrive_full(na % S);
   } else if (warp == 8) {
     // ================= MMA issue =================
     if (lane == 0) {
@@ -558,21 +587,29 @@ __global__ void __launch_bounds__(256) spconv_to_bf16_kernel(const float *__rest
   }
 }
 
-// ---- W preparation: Wt[k][n][c] = W[k][c * sc + n * sn] converted to the MMA dtype, zero padded -----------------------
+// ---- W preparation: W[k][c * sc + n * sn] converted to the MMA dtype, zero padded, laid out as the SHARED-MEMORY IMAGE the
+// MMA kernels use for a (kernel offset, NT-row tile) panel: [k][n / NT][atom][n % NT][128 B], the eight 16-byte chunks of a
+// row XOR-swizzled with the row (SWIZZLE_128B, K-major).  A panel is then one contiguous block per atom and the kernels
+// fetch it with TMA bulk copies instead of staging it through registers.
 template <int KIND>
 __global__ void __launch_bounds__(256) spconv_prep_weights_kernel(const float *__restrict__ W, uint8_t *__restrict__ Wt, int k_vol,
-                                                                  int kdim, int ndim, int k_pad, int n_rows_pad, int64_t sc,
+                                                                  int kdim, int ndim, int k_pad, int n_rows_pad, int NT, int64_t sc,
                                                                   int64_t sn, int64_t sk, int f16) {
+  constexpr int ES = (KIND == 0) ? 4 : 2;
   const int64_t total = (int64_t)k_vol * n_rows_pad * k_pad;
+  const int n_atoms = k_pad * ES / kAtomBytes, n_tiles = n_rows_pad / NT;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % k_pad);
     const int n = (int)((i / k_pad) % n_rows_pad);
     const int k = (int)(i / ((int64_t)k_pad * n_rows_pad));
     float v = 0.0f;
     if (c < kdim && n < ndim) v = __ldg(W + (int64_t)k * sk + (int64_t)c * sc + (int64_t)n * sn);
-    if (KIND == 0) reinterpret_cast<uint32_t *>(Wt)[i] = to_tf32(v);
-    else if (f16) reinterpret_cast<__half *>(Wt)[i] = __float2half_rn(v);
-    else reinterpret_cast<__nv_bfloat16 *>(Wt)[i] = __float2bfloat16_rn(v);
+    const int byte = c * ES, at = byte / kAtomBytes, c16 = (byte % kAtomBytes) >> 4, within = byte & 15;
+    const int nt = n / NT, nl = n % NT;
+    const size_t off = ((((size_t)k * n_tiles + nt) * n_atoms + at) * NT + nl) * kAtomBytes + (size_t)(((c16 ^ (nl & 7)) << 4) + within);
+    if (KIND == 0) *reinterpret_cast<uint32_t *>(Wt + off) = to_tf32(v);
+    else if (f16) *reinterpret_cast<__half *>(Wt + off) = __float2half_rn(v);
+    else *reinterpret_cast<__nv_bfloat16 *>(Wt + off) = __float2bfloat16_rn(v);
   }
 }
 
@@ -1092,9 +1129,9 @@ cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspac
   const int64_t total = (int64_t)p.k_vol * g.n_rows_pad * g.k_pad;
   const int prep_blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   if (p.precision == SPCONV_TF32)
-    spconv_prep_weights_kernel<0><<<prep_blocks, 256, 0, stream>>>(p.W, Wt, p.k_vol, p.kdim, p.ndim, g.k_pad, g.n_rows_pad, p.w_sc, p.w_sn, p.w_sk, a.f16);
+    spconv_prep_weights_kernel<0><<<prep_blocks, 256, 0, stream>>>(p.W, Wt, p.k_vol, p.kdim, p.ndim, g.k_pad, g.n_rows_pad, g.NT, p.w_sc, p.w_sn, p.w_sk, a.f16);
   else
-    spconv_prep_weights_kernel<1><<<prep_blocks, 256, 0, stream>>>(p.W, Wt, p.k_vol, p.kdim, p.ndim, g.k_pad, g.n_rows_pad, p.w_sc, p.w_sn, p.w_sk, a.f16);
+    spconv_prep_weights_kernel<1><<<prep_blocks, 256, 0, stream>>>(p.W, Wt, p.k_vol, p.kdim, p.ndim, g.k_pad, g.n_rows_pad, g.NT, p.w_sc, p.w_sn, p.w_sk, a.f16);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
   a.Wt = Wt; a.n_atoms = g.n_atoms; a.n_rows_pad = g.n_rows_pad; a.NT = g.NT; a.tmem_cols = g.tmem_cols;
