@@ -626,6 +626,20 @@ def main():
                             "(dgs_mcast_barrier: one multimem.red + spin, in mcast mode; the one-int NCCL all-reduce it replaced is timed "
                             "beside it); end to end = ms_per_step")
             del C_loc, panels
+        if world == 1:
+            # a cold-L2 figure beside the steady-state one.  Each step is preceded by a 512 MB write (4x the L2),
+            # timed per step with its own event pair so that the flush itself stays outside the measurement.
+            flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+            ts = []
+            for _ in range(5):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); step(); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            legs["cold_l2_ms_per_step"] = sorted(ts)[len(ts) // 2]
+            legs["cold_l2_note"] = "median of 5 steps, each after a 512 MB write that evicts the L2 (B and the first CSR bytes come from HBM)"
+            del flush
         if 512 % world == 0:
             n_s = 512 // world
             Bs = torch.rand(M, n_s, device=dev, generator=torch.Generator(dev).manual_seed(99 + rank))
