@@ -10,10 +10,11 @@
 //   sddmm_stages     DGS_SDDMM_STAGES          2 | 3 ring stages
 //   sddmm_chunk      DGS_SDDMM_CHUNK           edges per warp of the ring kernel (multiple of 32)
 //   sddmm_wpc        DGS_SDDMM_WPC             warps per CTA of the ring kernel
+//   spconv_ctas      DGS_SPCONV_CTAS           1 .. 3: persistent CTAs per SM of the pipelined spconv kernel (unset: as many as fit)
 #pragma once
 
 namespace dgs {
-enum Option { OPT_SPMM_ROWPAR = 0, OPT_SPMM_PANEL, OPT_SPMM_NO_PDL, OPT_SPMM_SEGS, OPT_SPMM_CHUNK_CAP, OPT_SDDMM_NO_RING, OPT_SDDMM_STAGES, OPT_SDDMM_CHUNK, OPT_SDDMM_WPC, OPT_COUNT };
+enum Option { OPT_SPMM_ROWPAR = 0, OPT_SPMM_PANEL, OPT_SPMM_NO_PDL, OPT_SPMM_SEGS, OPT_SPMM_CHUNK_CAP, OPT_SDDMM_NO_RING, OPT_SDDMM_STAGES, OPT_SDDMM_CHUNK, OPT_SDDMM_WPC, OPT_SPCONV_CTAS, OPT_COUNT };
 int option(Option o);                          // -1 when unset
 int set_option(const char *name, int value);   // value < 0 clears the override (back to the environment); 0 ok, -1 unknown name
 }  // namespace dgs

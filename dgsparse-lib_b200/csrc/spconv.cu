@@ -27,6 +27,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include "common.cuh"
+#include "options.h"
 #include "spmm.h"
 #include "spconv.h"
 
@@ -1141,8 +1142,16 @@ cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspac
   {
     const size_t stage_bytes = (size_t)g.n_atoms * kTileM * kAtomBytes, w_smem = (size_t)g.n_atoms * g.NT * kAtomBytes;
     const size_t stg_smem = (size_t)4 * 32 * (kStgCols + 4) * 4;   // scatter staging of the four epilogue warps
-    const size_t budget = 225u * 1024u;
-    int S = w_smem + stg_smem < budget ? (int)((budget - w_smem - stg_smem) / stage_bytes) : 0;
+    // Persistent CTAs per SM: as many (<= 3: 288 threads x 64 registers) as still leave every CTA two whole-K stages, its W panel and two TMEM accumulators
+    // (2 x tmem_cols of the SM's 512 columns).  One CTA per SM leaves the scatter — 4 warps issuing red.global.add.v4 —
+    // as the bottleneck: MinkUNet 64 -> 64 tf32 forward 58.4 us with one CTA per SM, 44.0 us with two.
+    int per_sm = 1, S = 0;
+    for (int c = 3; c >= 1; c--) {
+      if (option(OPT_SPCONV_CTAS) >= 1 && option(OPT_SPCONV_CTAS) <= 3 && c != option(OPT_SPCONV_CTAS)) continue;
+      const size_t budget = (size_t)(225 / c) * 1024u - (c > 1 ? 1024u : 0u);   // 1 KB per extra CTA is reserved by the driver
+      const int Sc = w_smem + stg_smem + 1024 < budget ? (int)((budget - w_smem - stg_smem - 1024) / stage_bytes) : 0;
+      if ((Sc >= 2 && c * 2 * g.tmem_cols <= 512) || c == 1) { per_sm = c; S = Sc; break; }
+    }
     if (S > kPipeMaxStages) S = kPipeMaxStages;
     bool pipe = S >= 2 && !getenv("DGS_SPCONV_NO_PIPE");
     if (pipe && p.precision != SPCONV_TF32) {   // converted (bf16 / fp16) feature copy lives behind the weights in the workspace
@@ -1162,7 +1171,7 @@ cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspac
     }
     if (pipe && a.feat != nullptr) {
       a.n_stages = S;
-      int ctas = device_sm_count() / g.grid_y;
+      int ctas = device_sm_count() * per_sm / g.grid_y;
       if (ctas < 1) ctas = 1;
       a.tiles_per_cta = (n_tiles + ctas - 1) / ctas;
       dim3 grid((n_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta, g.grid_y);
