@@ -879,7 +879,12 @@ struct WgradTcArgs {
   int m64_mode;       // experiment: TMEM row mapping hypothesis for M = 64 (1: lane = row, 2: 16 rows per quadrant)
 };
 
-__global__ void __launch_bounds__(160, 1) spconv_wgrad_tc_kernel(const WgradTcArgs g) {
+// 8 gather warps (16 pairs of a tile each) + 1 MMA warp: the gather is an instruction stream of ~70 instructions per 16-byte
+// chunk-row, and with 4 gather warps (one per scheduler) it alone set the pace: 107 us for every channel count up to 64.
+constexpr int kWgtGatherWarps = 16;
+constexpr int kWgtThreads = (kWgtGatherWarps + 1) * 32;
+constexpr int kWgtRows = kTileM / kWgtGatherWarps;   // pairs of a tile per gather warp
+__global__ void __launch_bounds__(kWgtThreads, 1) spconv_wgrad_tc_kernel(const WgradTcArgs g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t s_full[kWgtMaxStages], s_empty[kWgtMaxStages], s_accfull, s_accempty;
   __shared__ uint32_t s_tmem;
@@ -894,11 +899,20 @@ __global__ void __launch_bounds__(160, 1) spconv_wgrad_tc_kernel(const WgradTcAr
   const int tmem_cols = g.NBk <= 32 ? 32 : g.NBk <= 64 ? 64 : 128;
 
   if (tid == 0) {
-    for (int s = 0; s < S; s++) { mbar_init(&s_full[s], 128); mbar_init(&s_empty[s], 1); }
-    mbar_init(&s_accfull, 1); mbar_init(&s_accempty, 128);
+    for (int s = 0; s < S; s++) { mbar_init(&s_full[s], kWgtGatherWarps * 32); mbar_init(&s_empty[s], 1); }
+    mbar_init(&s_accfull, 1); mbar_init(&s_accempty, 128);   // the flush is done by warps 0-3 (one TMEM lane quadrant each)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(&s_tmem, (uint32_t)tmem_cols);
+  if (warp == kWgtGatherWarps) tmem_alloc(&s_tmem, (uint32_t)tmem_cols);
+  // Channels beyond c_in / c_out inside the MB x NBk block are zero in EVERY tile: clear the stages once and never touch
+  // those chunks again (MB is always 128: with c_in = 64 that is half of the X chunks, with c_in = 4 31 of 32 — the gather
+  // warps are instruction bound, ncu: 3 300 instructions per warp and tile, one warp per scheduler)
+  const int x_chunks = min(mblk * 8, (a.c_in - ci0 + 3) / 4), g_chunks = min(nblk * 8, (a.c_out - co0 + 3) / 4);
+  if (x_chunks < mblk * 8 || g_chunks < nblk * 8) {
+    for (uint32_t o = (uint32_t)tid * 16u; o < (uint32_t)S * stage_bytes; o += (uint32_t)kWgtThreads * 16u)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + o), "r"(0u) : "memory");
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -908,15 +922,17 @@ __global__ void __launch_bounds__(160, 1) spconv_wgrad_tc_kernel(const WgradTcAr
   const int t_begin = blockIdx.x * a.tiles_per_cta;
   const int n_my = max(0, min(n_tiles, t_begin + a.tiles_per_cta) - t_begin);
 
-  if (warp < 4) {
+  if (warp < kWgtGatherWarps) {
     // ================= gather (+ the rare flush) =================
-    const int cpr = (mblk + nblk) * 8;   // 16-byte chunks per pair: X block chunks first, then G block chunks
+    // live 16-byte chunks per pair: X chunks first, then G chunks (c_in, c_out are multiples of 4 on this path)
+    const int cpr = x_chunks + g_chunks;
+    const int items = kWgtRows * cpr;    // (pair, chunk) items of this warp per tile
     TileCursor cur;
     int next_in = -1, next_out = -1;
     if (n_my > 0) {
       cur.init(a, t_begin);
       cur.seek(a, t_begin);
-      const int p = cur.pbase + warp * 32 + lane;
+      const int p = cur.pbase + warp * kWgtRows + (lane % kWgtRows);
       if (p < cur.pend) { next_in = cur.identity ? p : __ldg(a.imap + p); next_out = cur.identity ? p : __ldg(a.omap + p); }
     }
     int na = 0, cur_k = -1, n_flush = 0;
@@ -926,6 +942,7 @@ __global__ void __launch_bounds__(160, 1) spconv_wgrad_tc_kernel(const WgradTcAr
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       fence_proxy_async_smem();
       for (; na < upto; na++) mbar_arrive(&s_full[na % S]);
+      if (warp >= 4) { n_flush++; return; }      // TMEM lane quadrants belong to warps 0-3
       mbar_wait(&s_accfull, (uint32_t)n_flush & 1u);
       tc_fence_after();
       int row = warp * 32 + lane;                // accumulator row (c_in index within the block) = TMEM lane
@@ -962,7 +979,7 @@ __global__ void __launch_bounds__(160, 1) spconv_wgrad_tc_kernel(const WgradTcAr
       const int tile_k = cur.offset(a);
       if (i + 1 < n_my) {
         cur.seek(a, t_begin + i + 1);
-        const int p = cur.pbase + warp * 32 + lane;
+        const int p = cur.pbase + warp * kWgtRows + (lane % kWgtRows);
         next_in = next_out = -1;
         if (p < cur.pend) { next_in = cur.identity ? p : __ldg(a.imap + p); next_out = cur.identity ? p : __ldg(a.omap + p); }
       }
@@ -974,18 +991,21 @@ __global__ void __launch_bounds__(160, 1) spconv_wgrad_tc_kernel(const WgradTcAr
       const uint32_t sX = base + (uint32_t)s * stage_bytes;
       int rl = lane / cpr, cc = lane % cpr;
       const int drl = 32 / cpr, dcc = 32 % cpr;
-      for (int it = 0; it < cpr; it++) {
-        const int r = warp * 32 + rl;
-        const bool is_x = cc < mblk * 8;
-        const int blk = is_x ? (cc >> 3) : ((cc - mblk * 8) >> 3), c = cc & 7;
+      for (int it = 0; it * 32 < items; it++) {
+        const bool live = it * 32 + lane < items;    // an odd chunk count leaves half of the last round without work
+        if (!live) rl = 0;
+        const int r = warp * kWgtRows + rl;
+        const bool is_x = cc < x_chunks;
+        const int idx = is_x ? cc : cc - x_chunks;
+        const int blk = idx >> 3, c = idx & 7;
         const int in_r = __shfl_sync(0xffffffffu, my_in, rl), out_r = __shfl_sync(0xffffffffu, my_out, rl);
         const int src_row = is_x ? in_r : out_r;   // (the select must happen in the READING lane)
         const int ch = (is_x ? ci0 : co0) + blk * 32 + c * 4;
-        const bool ok = src_row >= 0 && ch < (is_x ? a.c_in : a.c_out);
+        const bool ok = src_row >= 0;
         const float *src = is_x ? a.in + (int64_t)src_row * a.ld_in + ch : g.dout + (int64_t)src_row * g.ld_dout + ch;
         const uint32_t dst = sX + (uint32_t)((is_x ? 0 : mblk) + blk) * blk_bytes + (uint32_t)r * kAtomBytes +
                              (uint32_t)((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));   // BASE32B swizzle
-        cp_async16_zfill(dst, ok ? (const void *)src : (const void *)a.in, ok ? 16u : 0u);
+        if (live) cp_async16_zfill(dst, ok ? (const void *)src : (const void *)a.in, ok ? 16u : 0u);
         rl += drl; cc += dcc;
         if (cc >= cpr) { cc -= cpr; rl += 1; }
       }
@@ -1037,7 +1057,7 @@ __global__ void __launch_bounds__(160, 1) spconv_wgrad_tc_kernel(const WgradTcAr
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, (uint32_t)tmem_cols);
+  if (warp == kWgtGatherWarps) tmem_dealloc(tmem, (uint32_t)tmem_cols);
 }
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -1251,7 +1271,7 @@ cudaError_t spconv_wgrad(int k_vol, int c_in, int c_out, const int *kpos, const 
       const size_t smem = 1024 + (size_t)S * stage_bytes;
       if ((e = cudaFuncSetAttribute(spconv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
       dim3 grid((n_tiles + g.a.tiles_per_cta - 1) / g.a.tiles_per_cta, by, bz);
-      spconv_wgrad_tc_kernel<<<grid, 160, smem, stream>>>(g);
+      spconv_wgrad_tc_kernel<<<grid, kWgtThreads, smem, stream>>>(g);
       return cudaGetLastError();
     }
   }
