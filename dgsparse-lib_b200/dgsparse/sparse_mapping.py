@@ -33,11 +33,26 @@ class KernelMap:
     separate_mid: bool
 
 
-def _check_coords(c: torch.Tensor):
-    """The kernels pack a voxel into one 64-bit key, 16 bits per component: reject what would alias another voxel."""
+_ws = {}
+
+
+def _workspace(nbytes, device):
+    # scratch of the build (hash table, hit table, scan temporaries), reused per (device, stream): calls on one stream are ordered
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def _check_coords(c: torch.Tensor, ranges: bool = True):
+    """The kernels pack a voxel into one 64-bit key, 16 bits per component: reject what would alias another voxel.
+    ranges=False skips the value check (four reductions and a device->host read): build_kernel_map's kernels test every
+    coordinate themselves and report through the pair counts it reads back anyway."""
     if c.dtype != torch.int32 or c.dim() != 2 or c.size(1) != 4:
         raise TypeError("in_coords must be int32 [n, 4] = (batch, x, y, z)")
-    if c.size(0) == 0:
+    if c.size(0) == 0 or not ranges:
         return
     xyz, b = c[:, 1:], c[:, 0]
     lo, hi, bmin, bmax = (int(v) for v in torch.stack([xyz.amin(), xyz.amax(), b.amin(), b.amax()]).tolist())
@@ -101,8 +116,8 @@ def build_kernel_map(in_coords: torch.Tensor, kernel_size=3, stride=1, separate_
     ks, st = _triple(kernel_size), _triple(stride)
     pd = _triple(padding) if padding is not None else (0, 0, 0)
     c = in_coords.contiguous()
-    _check_coords(c)
     sub = st == (1, 1, 1) and padding is None
+    _check_coords(c, ranges=not sub)     # (the down-sampling / expansion kernels pack keys before anything is tested)
     if separate_mid and not sub:
         raise ValueError("separate_mid needs a submanifold layer (stride 1, padding None)")
     plain = pd == (0, 0, 0) and min_coord is None and max_coord is None and all(s in (1, k) for s, k in zip(st, ks))
@@ -116,16 +131,15 @@ def build_kernel_map(in_coords: torch.Tensor, kernel_size=3, stride=1, separate_
     k_vol = ks[0] * ks[1] * ks[2]
     with torch.cuda.device(c.device):
         dev = c.device
-        imap = torch.empty(k_vol * n_out, dtype=torch.int32, device=dev)
-        omap = torch.empty(k_vol * n_out, dtype=torch.int32, device=dev)
-        knnz = torch.zeros(k_vol, dtype=torch.int32, device=dev)
-        kpos = torch.zeros(k_vol + 1, dtype=torch.int32, device=dev)
-        qkpos = torch.zeros(k_vol + 1, dtype=torch.int32, device=dev)
-        ws = torch.empty(lib.dgs_kmap_workspace_bytes(n_in, n_out, k_vol), dtype=torch.uint8, device=dev)
+        maps = torch.empty(2, k_vol * n_out, dtype=torch.int32, device=dev)      # one allocation each for the maps and
+        imap, omap = maps[0], maps[1]
+        counts = torch.zeros(3 * k_vol + 2, dtype=torch.int32, device=dev)       # ... the three small count arrays
+        knnz, kpos, qkpos = counts[:k_vol], counts[k_vol:2 * k_vol + 1], counts[2 * k_vol + 1:]
+        ws = _workspace(lib.dgs_kmap_workspace_bytes(n_in, n_out, k_vol), dev)
         check(lib.dgs_kmap_build_ex(n_in, ptr(c), n_out, ptr(out_coords), ks[0], ks[1], ks[2], st[0], st[1], st[2],
                                     pd[0], pd[1], pd[2], int(sub), q, int(separate_mid), ptr(imap), ptr(omap), ptr(knnz),
                                     ptr(kpos), ptr(qkpos), ptr(ws), ws.numel(), stream_of(c)), "dgs_kmap_build_ex")
-        ends = torch.stack([kpos[-1], qkpos[-1]]).cpu()
+        ends = counts[2 * k_vol::k_vol + 1].cpu()      # kpos[-1], qkpos[-1]: the one device->host read of the build
     pairs, sum_nnz = int(ends[0]), int(ends[1])
     if pairs < 0:   # the kernels found a coordinate outside the 16-bit key range (dgs_kmap_build_ex poisons kpos with -1)
         raise ValueError("kernel map: a coordinate does not fit the 16-bit-per-component voxel key")
