@@ -13,6 +13,7 @@
 // int32 CSR->CSC permutation (q10), mean backward wrt dense scaled by the degree of the SOURCE row.
 #include <ATen/ATen.h>
 #include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGraphsC10Utils.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/autograd.h>
 #include <torch/library.h>
@@ -32,19 +33,38 @@ void check(int rc, const char *what) { TORCH_CHECK(rc == 0, what, " failed: ", d
 void require_cuda(const Tensor &t, const char *name) {
   TORCH_CHECK(t.is_cuda(), "dgsparse (B200) ops need CUDA tensors; there is no CPU path (", name, " is on ", t.device(), ")");
 }
+// (every microsecond counts on the reference's own benchmark shape — a Cora-sized graph, ~12 us per call — so the common
+//  case of an already contiguous tensor does not go through the dispatcher)
 Tensor i32c(const Tensor &t, const char *name) {
   require_cuda(t, name);
   TORCH_CHECK(t.scalar_type() == at::kInt, name, " must be int32 (got ", t.scalar_type(), ")");   // dgsparse/storage.py:27-82
-  return t.contiguous();
+  return t.is_contiguous() ? t : t.contiguous();
 }
 Tensor f32c(const Tensor &t, const char *name) {
   require_cuda(t, name);
   TORCH_CHECK(t.scalar_type() == at::kFloat, name, " must be float32 (got ", t.scalar_type(), ")");
-  return t.contiguous();
+  return t.is_contiguous() ? t : t.contiguous();
 }
 void *stream_of(const Tensor &t) { return at::cuda::getCurrentCUDAStream(t.get_device()).stream(); }
+// Kernel scratch.  Small requests reuse one buffer per (thread, device, stream) — work on one stream is ordered, so the next
+// call may overwrite it — instead of paying a caching-allocator round trip per call; large ones, and anything inside a
+// CUDA-graph capture (the graph must own its memory), are allocated per call.
 Tensor scratch(size_t bytes, const Tensor &like) {
-  return at::empty({(int64_t)(bytes < 256 ? 256 : bytes)}, like.options().dtype(at::kByte));
+  const int64_t n = (int64_t)(bytes < 256 ? 256 : bytes);
+  constexpr int64_t kCached = 8 << 20;
+  if (n > kCached || c10::cuda::currentStreamCaptureStatusMayInitCtx() != c10::cuda::CaptureStatus::None)
+    return at::empty({n}, like.options().dtype(at::kByte));
+  struct Slot { int device = -1; void *stream = nullptr; Tensor buf; };
+  static thread_local Slot slots[4];
+  static thread_local int next = 0;
+  const int device = like.get_device();
+  void *stream = stream_of(like);
+  for (Slot &sl : slots)
+    if (sl.device == device && sl.stream == stream && sl.buf.defined() && sl.buf.numel() >= n) return sl.buf;
+  Slot &sl = slots[next++ % 4];
+  sl.device = device; sl.stream = stream;
+  sl.buf = at::empty({n < (1 << 20) ? (int64_t)(1 << 20) : n}, like.options().dtype(at::kByte));
+  return sl.buf;
 }
 const int *iptr(const Tensor &t) { return t.defined() ? t.data_ptr<int>() : nullptr; }
 const float *fptr(const Tensor &t) { return t.defined() ? t.data_ptr<float>() : nullptr; }
@@ -56,7 +76,8 @@ Tensor spmm_fwd(const Tensor &rowptr_, const Tensor &col_, const Tensor &values_
   TORCH_CHECK(dense.dim() == 2, "dense must be 2-D [K, N]");
   Tensor values;
   if (values_.defined()) {
-    values = f32c(values_, "values").reshape({-1});
+    values = f32c(values_, "values");
+    if (values.dim() != 1) values = values.reshape({-1});
     TORCH_CHECK(values.numel() == col.numel(), "values must have one entry per nonzero");
   }
   const int64_t M = rowptr.numel() - 1, N = dense.size(1), nnz = col.numel();
