@@ -680,17 +680,22 @@ __global__ void __launch_bounds__(256) spconv_fgms_simt_kernel(const SpconvArgs 
 // The warp-per-4-pairs kernel above re-reads W[k] for every 4 pairs and runs at ~3 TFLOP/s (0.82 ms on the MinkUNet 64 -> 64
 // layer, where the reference's _fgms_fusion_fp32 takes 0.10 ms on the same B200: profiles/r02_spconv_vs_reference.jsonl).
 // This one is a plain register-blocked SGEMM on gathered tiles: a CTA of 256 threads owns one tile of 128 pairs (one offset)
-// x 64 output channels and walks c_in in chunks of 32: the gathered rows go to shared memory TRANSPOSED (channel-major, so
+// x 64 (or 32) output channels and walks c_in in chunks of 32: the gathered rows go to shared memory TRANSPOSED (channel-major, so
 // that a thread reads its 8 pairs of one channel with two 16-byte loads), the W[k] chunk row-major; thread (ty, tx)
 // accumulates an 8 x 4 block with fp32 FMAs, c_in ascending (the order of cpu_compute), and the block is scattered with
 // red.global.add.v4.f32.  32 FMAs per 3 shared-memory loads; several CTAs per SM hide the gather.
-constexpr int kFtN = 64, kFtK = 32, kFtLdA = kTileM + 4;
+// RT = pairs per thread: 8 -> 16 x 16 threads own 128 pairs x 64 channels; 4 -> 32 x 8 threads 128 x 32; 2 -> 64 x 4 threads 128 x 16 (layers
+// with c_out <= 32 / 16, where the 64-wide block multiplied zeros for half of its columns: 32 -> 32 forward 56 us against 45 us for the
+// reference's kernel).
+constexpr int kFtK = 32, kFtLdA = kTileM + 4;
+template <int RT>
 __global__ void __launch_bounds__(256) spconv_fgms_fp32_tiled_kernel(const SpconvArgs a, const float *__restrict__ W, int64_t w_sc,
                                                                      int64_t w_sn, int64_t w_sk, int out_vec4) {
   __shared__ __align__(16) float sA[kFtK][kFtLdA];
+  constexpr int TXN = 2 * RT, kFtN = TXN * 4;      // RT = 8 | 4 | 2 pairs per thread -> 16 | 8 | 4 thread columns of 4 channels = 64 | 32 | 16
   __shared__ __align__(16) float sW[kFtK][kFtN];
   __shared__ int s_in[kTileM], s_out[kTileM];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
   const int tile = blockIdx.x, co0 = blockIdx.y * kFtN;
   int k;
   if (tile < a.n_map_tiles) {
@@ -709,9 +714,9 @@ __global__ void __launch_bounds__(256) spconv_fgms_fp32_tiled_kernel(const Spcon
   }
   __syncthreads();
   const float *Wk = W + (int64_t)k * w_sk;
-  float acc[8][4];
+  float acc[RT][4];
 #pragma unroll
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < RT; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
 
@@ -738,13 +743,21 @@ __global__ void __launch_bounds__(256) spconv_fgms_fp32_tiled_kernel(const Spcon
     __syncthreads();
 #pragma unroll 8
     for (int ci = 0; ci < kFtK; ci++) {
-      const float4 a0 = *reinterpret_cast<const float4 *>(&sA[ci][ty * 8]);
-      const float4 a1 = *reinterpret_cast<const float4 *>(&sA[ci][ty * 8 + 4]);
+      float av[RT];
+      if (RT == 2) {
+        const float2 t = *reinterpret_cast<const float2 *>(&sA[ci][ty * RT]);
+        av[0] = t.x; av[1] = t.y;
+      } else {
+#pragma unroll
+        for (int h = 0; h < RT / 4; h++) {
+          const float4 t = *reinterpret_cast<const float4 *>(&sA[ci][ty * RT + 4 * h]);
+          av[4 * h] = t.x; av[4 * h + 1] = t.y; av[4 * h + 2] = t.z; av[4 * h + 3] = t.w;
+        }
+      }
       const float4 w = *reinterpret_cast<const float4 *>(&sW[ci][tx * 4]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
       const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int i = 0; i < 8; i++)
+      for (int i = 0; i < RT; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
     }
@@ -753,8 +766,8 @@ __global__ void __launch_bounds__(256) spconv_fgms_fp32_tiled_kernel(const Spcon
   const int co = co0 + tx * 4;
   if (co >= a.c_out) return;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int orow = s_out[ty * 8 + i];
+  for (int i = 0; i < RT; i++) {
+    const int orow = s_out[ty * RT + i];
     if (orow < 0) continue;
     float *dst = a.out + (int64_t)orow * a.ld_out + co;
     if (out_vec4) red_add_v4(dst, acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -1133,8 +1146,16 @@ cudaError_t spconv_gemm(const SpconvProblem &p, void *workspace, size_t workspac
     const bool in_vec4 = p.kdim % 4 == 0 && p.ld_in % 4 == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0;
     if (in_vec4 && !getenv("DGS_SPCONV_FP32_SIMPLE")) {
       const int out_vec4 = p.ndim % 4 == 0 && p.ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
-      dim3 grid(n_tiles, (p.ndim + kFtN - 1) / kFtN);
-      spconv_fgms_fp32_tiled_kernel<<<grid, 256, 0, stream>>>(a, p.W, p.w_sc, p.w_sn, p.w_sk, out_vec4);
+      if (p.ndim <= 16) {
+        dim3 grid(n_tiles, 1);
+        spconv_fgms_fp32_tiled_kernel<2><<<grid, 256, 0, stream>>>(a, p.W, p.w_sc, p.w_sn, p.w_sk, out_vec4);
+      } else if (p.ndim <= 32) {
+        dim3 grid(n_tiles, 1);
+        spconv_fgms_fp32_tiled_kernel<4><<<grid, 256, 0, stream>>>(a, p.W, p.w_sc, p.w_sn, p.w_sk, out_vec4);
+      } else {
+        dim3 grid(n_tiles, (p.ndim + 63) / 64);
+        spconv_fgms_fp32_tiled_kernel<8><<<grid, 256, 0, stream>>>(a, p.W, p.w_sc, p.w_sn, p.w_sk, out_vec4);
+      }
       return cudaGetLastError();
     }
     const int64_t warps = (int64_t)n_tiles * (kTileM / kSimtPairs);
