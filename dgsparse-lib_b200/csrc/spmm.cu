@@ -281,11 +281,14 @@ static int pick_chunk(int N, int64_t nnz, bool with_arg, int G, int blocks_per_s
   // and 30.7 | 26.4 | 32.9.
   // Only while the GPU is underfilled, though: once 64-nnz segments give every resident group one (arxiv-like, 1.17 M nnz),
   // halving them only doubles the per-segment overhead (N=32 0.065 -> 0.088 ms).
+  // Between the two (arxiv-like, 1.17 M nnz): ONE wave of blocks over all column panels, every resident group one segment —
+  // a fixed 64-nnz segment left 1.28 waves at N = 32 (58.6 us against 45) and 2.56 at N = 128 (135 us against 114).
   if (chunk < 2 * kBatch) {
     const int min_chunk = (N <= 64) ? kBatch : 2 * kBatch;
-    chunk = nnz / resident_groups;
+    const int panels = (N + 4 * G - 1) / (4 * G);
+    const int64_t per_panel = resident_groups / panels > 0 ? resident_groups / panels : 1;
+    chunk = (nnz + per_panel - 1) / per_panel;
     if (chunk < min_chunk) chunk = min_chunk;
-    if (chunk > 2 * kBatch) chunk = 2 * kBatch;
   }
   int cap = option(OPT_SPMM_CHUNK_CAP);
   if (cap < 64) cap = 16384;
