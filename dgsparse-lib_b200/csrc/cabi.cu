@@ -119,6 +119,33 @@ __global__ void __launch_bounds__(256) spmm_colmajor_kernel(int M, int N, int K,
   C[(size_t)n * M + r] = acc;
 }
 
+// out[c, r] = in[r, c] for a row-major in[rows, cols]: 32 x 32 tiles through shared memory, both sides coalesced.  The
+// tile index is linear in blockIdx.x (either dimension may exceed the 65 535 limit of grid.y: products-like M = 2.4 M).
+__global__ void __launch_bounds__(256) transpose_tiles_kernel(const float *__restrict__ in, int rows, int cols, float *__restrict__ out) {
+  __shared__ float tile[32][33];
+  const int tiles_c = (cols + 31) / 32;
+  const int tr = blockIdx.x / tiles_c, tc = blockIdx.x - tr * tiles_c;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = tr * 32 + ty + i, c = tc * 32 + tx;
+    if (r < rows && c < cols) tile[ty + i][tx] = __ldg(in + (size_t)r * cols + c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = tc * 32 + ty + i, r = tr * 32 + tx;
+    if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[tx][ty + i];
+  }
+}
+cudaError_t transpose_tiles(const float *in, int rows, int cols, float *out, cudaStream_t s) {
+  const int64_t tiles = (int64_t)((rows + 31) / 32) * ((cols + 31) / 32);
+  if (tiles <= 0) return cudaSuccess;
+  if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+  transpose_tiles_kernel<<<(unsigned)tiles, 256, 0, s>>>(in, rows, cols, out);
+  return cudaGetLastError();
+}
+
 // rowptr[r] = first position p with rowIdx[p] >= r (rowIdx ascending): one binary search per row
 __global__ void __launch_bounds__(256) coo_to_rowptr_kernel(const int *__restrict__ rowIdx, int nnz, int nr, int *__restrict__ rowptr) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,6 +206,9 @@ int dgs_sm_count(void) { return dgs::device_sm_count(); }
 int dgs_spmm_last_path(void) { return dgs::spmm_last_path(); }
 int dgs_set_option(const char *name, int value) { return dgs::set_option(name, value); }
 void dgs_spmm_forget_graph_notes(void) { dgs::spmm_forget_graph_notes(); }
+void dgs_sddmm_last_geometry(int *warps_per_cta, int *ctas_per_sm, int *edges_per_warp) {
+  dgs::sddmm_last_geometry(warps_per_cta, ctas_per_sm, edges_per_warp);
+}
 
 size_t dgs_spmm_workspace_bytes(int N, int64_t nnz, int with_arg) {
   return dgs::spmm_workspace_bytes(N, nnz, with_arg != 0);
@@ -667,8 +697,17 @@ int dgs_profile_collect(int max_records, int *kernel_ids, float *ms) { return dg
 
 void gespmmCsrSpMM(const SpMatCsrDescr_t A, float *B, const int N, float *C, bool transpose_BC, gespmmAlg_t alg) {
   (void)alg;  // every reference algorithm computes the same C; one kernel serves them all
-  if (!transpose_BC) {
-    if (A.nrow <= 0 || N <= 0) return;
+  if (A.nrow <= 0 || N <= 0) return;
+  // Column-major operands (transpose_BC = false: ldB = ncol, ldC = nrow; src/ge-spmm/csrspmm_non_transpose.cu): the row-major
+  // kernel between two tiled transposes — B^T in, C^T out through the legacy scratch — which costs 2 x 8 bytes per dense
+  // element of HBM traffic instead of an uncoalesced 4-byte gather per nonzero and output element.  Measured against the
+  // one-thread-per-element kernel it replaces (tools/exp_colmajor.py, profiles/r02_exp_colmajor.jsonl): p2p-Gnutella31 N = 32
+  // 27.3 vs 29.3 us, arxiv-like N = 32 / 128 0.067 / 0.184 vs 1.11 / 1.92 ms, a quarter-size reddit-like matrix at N = 64
+  // 0.42 vs 13.2 ms (the reference's best non-transposed algorithm: 34.6 us, 0.75 / 1.36 ms, 4.37 ms).  The simple kernel
+  // remains for a descriptor without ncol (B cannot be sized) and behind spmm_colmajor = 0.
+  bool colmajor_naive = false;
+  if (!transpose_BC) colmajor_naive = dgs::option(dgs::OPT_SPMM_COLMAJOR) == 0 || A.ncol <= 0;
+  if (colmajor_naive) {
     dim3 grid((A.nrow + 255) / 256, N);
     spmm_colmajor_kernel<<<grid, 256, 0, 0>>>(A.nrow, N, A.ncol, A.indptr, A.indices, A.data, B, C);
     legacy_report(ok_or(cudaGetLastError(), "gespmmCsrSpMM(colmajor)"), "gespmmCsrSpMM");
@@ -685,9 +724,23 @@ void gespmmCsrSpMM(const SpMatCsrDescr_t A, float *B, const int N, float *C, boo
     if (hint > 0) { p.nnz_on_device = true; p.nnz_report = report; }
   }
   const size_t need = dgs::spmm_workspace_bytes(N, p.nnz, false);
+  const size_t ws_bytes = (need + 255) / 256 * 256;
+  const size_t bt_bytes = transpose_BC ? 0 : ((size_t)A.ncol * N * 4 + 255) / 256 * 256;
+  const size_t ct_bytes = transpose_BC ? 0 : ((size_t)A.nrow * N * 4 + 255) / 256 * 256;
   void *ws = nullptr;
-  cudaError_t e = legacy_scratch(need, &ws);
+  cudaError_t e = legacy_scratch(ws_bytes + bt_bytes + ct_bytes, &ws);
   if (e != cudaSuccess) { legacy_report(fail(e, "gespmmCsrSpMM(scratch)"), "gespmmCsrSpMM"); return; }
+  if (!transpose_BC) {
+    float *Bt = reinterpret_cast<float *>(static_cast<char *>(ws) + ws_bytes);
+    float *Ct = reinterpret_cast<float *>(static_cast<char *>(ws) + ws_bytes + bt_bytes);
+    // column-major B[ncol, N] is a row-major [N, ncol] array: transpose it to the row-major [ncol, N] the kernel gathers from
+    if ((e = transpose_tiles(B, N, A.ncol, Bt, nullptr)) != cudaSuccess) { legacy_report(fail(e, "gespmmCsrSpMM(B transpose)"), "gespmmCsrSpMM"); return; }
+    p.B = Bt; p.dst[0] = Ct;
+    int rc = ok_or(dgs::spmm_csr(p, ws, need, nullptr), "gespmmCsrSpMM");
+    if (rc == 0) rc = ok_or(transpose_tiles(Ct, A.nrow, N, C, nullptr), "gespmmCsrSpMM(C transpose)");
+    legacy_report(rc, "gespmmCsrSpMM");
+    return;
+  }
   legacy_report(ok_or(dgs::spmm_csr(p, ws, need, nullptr), "gespmmCsrSpMM"), "gespmmCsrSpMM");
 }
 

@@ -63,9 +63,11 @@ template <int G, int NV> __device__ __forceinline__ int edge_slot(int gl) {
   return slot;
 }
 
-template <int VEC, int G, bool COO, bool MEAN, bool MASK>
-__global__ void __launch_bounds__(kSdThreads) sddmm_kernel(const SddmmArgs a) {
-  constexpr int GPB = kSdThreads / G;
+// THREADS: lane groups never talk to each other, so the CTA size only sets the granularity in which an SM's slots are handed
+// out and taken back (see the ring kernel's one-warp CTAs below)
+template <int VEC, int G, bool COO, bool MEAN, bool MASK, int THREADS>
+__global__ void __launch_bounds__(THREADS) sddmm_kernel(const SddmmArgs a) {
+  constexpr int GPB = THREADS / G;
   constexpr int PER = kSdBatch / G;
   constexpr int NV = (G < kSdU) ? G : kSdU;       // edges reduced together
   __shared__ int s_col[GPB][kSdBatch + 1];
@@ -378,8 +380,10 @@ __global__ void __launch_bounds__(512, 1) sddmm_ring_kernel(const SddmmRingArgs 
 
 constexpr int kRingSmemOptIn = 227 * 1024;   // the most a CTA may ask for on sm_100; rings use <= ~200 KB
 
+// occ_out != nullptr: no launch, *occ_out = CTAs of this geometry (g.wpc warps, smem bytes) one SM really holds — the
+// registers of the instantiation, the ring's shared memory and the thread limit together — the last answer cached per device.
 template <int KCH, int STAGES>
-static cudaError_t launch_ring(const SddmmRingArgs &g, int grid, size_t smem, bool coo, bool mean, cudaStream_t s) {
+static cudaError_t launch_ring(const SddmmRingArgs &g, int grid, size_t smem, bool coo, bool mean, cudaStream_t s, int *occ_out) {
   cudaError_t e;
   const bool fullk = g.a.K == 128 * KCH;
   // the opt-in to > 48 KB of dynamic shared memory is per kernel and per device, not per launch: set it once (a
@@ -387,12 +391,26 @@ static cudaError_t launch_ring(const SddmmRingArgs &g, int grid, size_t smem, bo
 #define DGS_RING(FULL_, COO_, MEAN_)                                                                                       \
   do {                                                                                                                     \
     static bool optin[64] = {false};                                                                                       \
+    static int occ_wpc[64] = {0}, occ_n[64] = {0};                                                                         \
+    static size_t occ_smem[64] = {0};                                                                                      \
     int dev_ = 0;                                                                                                          \
     if ((e = cudaGetDevice(&dev_)) != cudaSuccess) return e;                                                               \
     if (dev_ < 0 || dev_ >= 64 || !optin[dev_]) {                                                                          \
       if ((e = cudaFuncSetAttribute(sddmm_ring_kernel<KCH, STAGES, FULL_, COO_, MEAN_>,                                    \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmemOptIn)) != cudaSuccess) return e; \
       if (dev_ >= 0 && dev_ < 64) optin[dev_] = true;                                                                      \
+    }                                                                                                                      \
+    if (occ_out != nullptr) {                                                                                              \
+      const bool slot_ = dev_ >= 0 && dev_ < 64;                                                                           \
+      int n_ = -1;                                                                                                         \
+      if (slot_ && occ_wpc[dev_] == g.wpc && occ_smem[dev_] == smem) n_ = occ_n[dev_];                                     \
+      if (n_ < 0) {                                                                                                        \
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n_, sddmm_ring_kernel<KCH, STAGES, FULL_, COO_, MEAN_>,    \
+                                                               g.wpc * 32, smem)) != cudaSuccess) return e;                \
+        if (slot_) { occ_wpc[dev_] = 0; occ_smem[dev_] = smem; occ_n[dev_] = n_; occ_wpc[dev_] = g.wpc; }                  \
+      }                                                                                                                    \
+      *occ_out = n_;                                                                                                       \
+      return cudaSuccess;                                                                                                  \
     }                                                                                                                      \
     sddmm_ring_kernel<KCH, STAGES, FULL_, COO_, MEAN_><<<grid, g.wpc * 32, smem, s>>>(g);                                  \
   } while (0)
@@ -409,15 +427,23 @@ static cudaError_t launch_ring(const SddmmRingArgs &g, int grid, size_t smem, bo
   return cudaGetLastError();
 }
 
+template <int VEC, int G, int THREADS>
+static cudaError_t launch_gt(const SddmmArgs &a, bool coo, bool mean, bool mask, cudaStream_t s) {
+  const int gpb = THREADS / G;
+  const int grid = (a.num_chunks + gpb - 1) / gpb;
+  if (coo) sddmm_kernel<VEC, G, true, false, false, THREADS><<<grid, THREADS, 0, s>>>(a);
+  else if (mask) sddmm_kernel<VEC, G, false, false, true, THREADS><<<grid, THREADS, 0, s>>>(a);
+  else if (mean) sddmm_kernel<VEC, G, false, true, false, THREADS><<<grid, THREADS, 0, s>>>(a);
+  else sddmm_kernel<VEC, G, false, false, false, THREADS><<<grid, THREADS, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
 template <int VEC, int G>
 static cudaError_t launch_g(const SddmmArgs &a, bool coo, bool mean, bool mask, cudaStream_t s) {
-  const int gpb = kSdThreads / G;
-  const int grid = (a.num_chunks + gpb - 1) / gpb;
-  if (coo) sddmm_kernel<VEC, G, true, false, false><<<grid, kSdThreads, 0, s>>>(a);
-  else if (mask) sddmm_kernel<VEC, G, false, false, true><<<grid, kSdThreads, 0, s>>>(a);
-  else if (mean) sddmm_kernel<VEC, G, false, true, false><<<grid, kSdThreads, 0, s>>>(a);
-  else sddmm_kernel<VEC, G, false, false, false><<<grid, kSdThreads, 0, s>>>(a);
-  return cudaGetLastError();
+  // 64-thread CTAs: 3 - 16 % faster than 256 wherever a row is shorter than 256 B, level above (tools/exp_sddmm_threads.py,
+  // profiles/r02_exp_sddmm_threads.jsonl: arxiv-like K = 16 / 32 / 48 34.4 / 43.2 / 84.7 -> 29.0 / 39.2 / 77.9 us)
+  if (option(OPT_SDDMM_THREADS) == 256) return launch_gt<VEC, G, kSdThreads>(a, coo, mean, mask, s);
+  return launch_gt<VEC, G, 64>(a, coo, mean, mask, s);
 }
 
 template <int VEC> static cudaError_t launch_v(int G, const SddmmArgs &a, bool coo, bool mean, bool mask, cudaStream_t s) {
@@ -427,6 +453,13 @@ template <int VEC> static cudaError_t launch_v(int G, const SddmmArgs &a, bool c
   case 16: return launch_g<VEC, 16>(a, coo, mean, mask, s);
   default: return launch_g<VEC, 32>(a, coo, mean, mask, s);
   }
+}
+
+static thread_local int g_last_geo[3] = {0, 0, 0};
+void sddmm_last_geometry(int *wpc, int *ctas_per_sm, int *chunk) {
+  if (wpc) *wpc = g_last_geo[0];
+  if (ctas_per_sm) *ctas_per_sm = g_last_geo[1];
+  if (chunk) *chunk = g_last_geo[2];
 }
 
 cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
@@ -440,7 +473,7 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
   // rows of 256 B .. 4 KB made of aligned 16-byte chunks: shared-memory ring kernel
   // latency regime (< 1 M edges) at K = 64: one 16-lane pass of the register kernel beats the ring's set-up
   // (ca-CondMat 19.1 vs 26.8 us, p2p-Gnutella31 14.7 vs 16.7 us; at K >= 128 the ring is level or ahead)
-  const bool small_k64 = p.K == 64 && p.nnz < (1 << 20);
+  const bool small_k64 = p.K == 64 && p.nnz < (1 << 20) && option(OPT_SDDMM_NO_RING) != 0;   // sddmm_no_ring = 0 forces the ring
   if (vec4 && !mask && p.K >= 64 && p.K <= 1024 && !small_k64 && option(OPT_SDDMM_NO_RING) != 1) {
     SddmmRingArgs g;
     SddmmArgs &a = g.a;
@@ -449,28 +482,56 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
     a.D1 = p.D1; a.D2 = p.D2; a.ld1 = p.ld1; a.ld2 = p.ld2;
     a.E = nullptr; a.out = p.out;
     g.slot_bytes = ((uint32_t)p.K * 4u + 127u) & ~127u;
-    // ring geometry: 4 edges per batch, STAGES batches per warp ring; as many warps as ~200 KB of ring allow
+    // ring geometry: 4 edges per batch, STAGES batches per warp ring.  The warps of the ring kernel never talk to each other,
+    // so the CTA is only the unit in which an SM's registers and shared memory are handed out and taken back: with ONE warp
+    // per CTA a finished warp's ring goes to the next chunk at once instead of waiting for the slowest warp of its CTA, and
+    // the SM holds as many rings as fit (13 at K = 256 instead of 12, 24 at K = 128 instead of 22, 28 at K = 64).  Measured
+    // (tools/exp_sddmm_ring.py, profiles/r02_exp_sddmm_ring.jsonl; 1 .. 16 warps per CTA, the residency from the occupancy
+    // API): arxiv-like K = 64 / 128 / 256 / 512 0.084 / 0.098 / 0.186 / 0.386 -> 0.077 / 0.090 / 0.170 / 0.373 ms, ca-CondMat
+    // K = 256 32.4 -> 26.8 us (the last line that trailed the reference's kernel, 29.1 us).
     int STAGES = 2;
     if (option(OPT_SDDMM_STAGES) == 3) STAGES = 3;
     g.warp_bytes = (uint32_t)STAGES * 2u * kRgNB * g.slot_bytes + (uint32_t)kRgMetaBytes;
     g.warp_bytes = (g.warp_bytes + 127u) & ~127u;
-    int wpc = (int)((200u * 1024u) / g.warp_bytes);
-    if (wpc > 16) wpc = 16;
-    // rows of <= 512 B: two CTAs of 11 warps fit one SM (90 registers x 704 threads, 2 x 11 rings <= 220 KB) = 22 resident
-    // warps instead of 16
-    int ctas_per_sm = 1;
-    if (2u * 11u * g.warp_bytes <= 220u * 1024u && option(OPT_SDDMM_WPC) != 16) { wpc = 11; ctas_per_sm = 2; }
-    if (option(OPT_SDDMM_WPC) >= 1 && option(OPT_SDDMM_WPC) <= 16 && (size_t)option(OPT_SDDMM_WPC) * g.warp_bytes <= 220u * 1024u) {
+    int wpc = g.warp_bytes <= 220u * 1024u ? 1 : 0;
+    if (option(OPT_SDDMM_WPC) >= 1 && option(OPT_SDDMM_WPC) <= 16 && (size_t)option(OPT_SDDMM_WPC) * g.warp_bytes <= 220u * 1024u)
       wpc = option(OPT_SDDMM_WPC);
-      ctas_per_sm = (2 * wpc * 32 * 90 <= 65536 && 2u * wpc * g.warp_bytes <= 220u * 1024u) ? 2 : 1;
-    }
     if (wpc >= 1) {
       g.wpc = wpc;
+      const size_t smem = (size_t)wpc * g.warp_bytes;
+      const bool mean = p.mean != 0 && !coo;
+      // one ring geometry, two uses: the occupancy query (occ != nullptr) and the launch
+      auto ring = [&](int grid, int *occ) -> cudaError_t {
+#define DGS_RING_GEO(KCH_)                                                                         \
+  do {                                                                                             \
+    if (STAGES == 3) return launch_ring<KCH_, 3>(g, grid, smem, coo, mean, stream, occ);           \
+    return launch_ring<KCH_, 2>(g, grid, smem, coo, mean, stream, occ);                            \
+  } while (0)
+        if (p.K <= 128) DGS_RING_GEO(1);
+        if (p.K <= 256) DGS_RING_GEO(2);
+        if (p.K <= 512) DGS_RING_GEO(4);
+        DGS_RING_GEO(8);
+#undef DGS_RING_GEO
+      };
+      // CTAs one SM really holds (registers of the instantiation, ring bytes, thread limit): the wave arithmetic below is
+      // only as good as this number
+      int ctas_per_sm = 1;
+      cudaError_t eo = ring(0, &ctas_per_sm);
+      if (eo != cudaSuccess) return eo;
+      if (ctas_per_sm < 1) ctas_per_sm = 1;
       const int64_t resident_warps = (int64_t)device_sm_count() * wpc * ctas_per_sm;
-      // Edges per warp: the grid should be a WHOLE number of waves of resident warps (one CTA of wpc warps per SM).  Large
-      // inputs: ~6 warps per resident warp for dynamic balance, the chunk rounded up to whole 4-edge batches so that the
-      // warps fill 6 waves (arxiv@256: 128-edge chunks gave 5.13 waves = 6 at 86 %).
+      // Edges per warp.  Large inputs: ~6 chunks per resident warp for dynamic balance.  When that would cut chunks shorter
+      // than ~144 edges (arxiv-like: 1.17 M edges on 1 924 .. 4 144 resident warps) the per-chunk costs — the row search, the
+      // ring's fill and drain — show: take chunks of ~144 edges instead, sized so that the grid is a whole number of waves
+      // of resident warps (tools/exp_sddmm_ring.py --chunks, profiles/r02_exp_sddmm_ring_chunks.jsonl: arxiv-like K = 64
+      // 48 -> 96 .. 160 edges 0.0777 -> 0.072 ms, K = 128 56 -> 128 .. 192 0.0906 -> 0.084 ms, K = 256 / 512 flat between 64 and
+      // 220; 256 and more lose again, and a ragged last wave costs ~7 %).
       int64_t chunk = (p.nnz + resident_warps * 6 - 1) / (resident_warps * 6);
+      if (chunk < 144) {
+        int64_t waves = (p.nnz + resident_warps * 72) / (resident_warps * 144);   // nearest whole number of waves
+        if (waves < 1) waves = 1;
+        chunk = (p.nnz + resident_warps * waves - 1) / (resident_warps * waves);
+      }
       if (chunk > 8192) chunk = 8192;
       chunk = (chunk + kRgNB - 1) / kRgNB * kRgNB;
       // Latency regime (a few waves of warps at most): a warp walks its edges 4 at a time, so the call takes
@@ -490,19 +551,9 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
       a.chunk = (int)chunk;
       a.num_chunks = (int)((p.nnz + a.chunk - 1) / a.chunk);
       const int grid = (a.num_chunks + wpc - 1) / wpc;
-      const size_t smem = (size_t)wpc * g.warp_bytes;
-      const bool mean = p.mean != 0 && !coo;
+      g_last_geo[0] = wpc; g_last_geo[1] = ctas_per_sm; g_last_geo[2] = a.chunk;
       ProfileScope prof(3, stream);
-#define DGS_RING_GEO(KCH_)                                                                    \
-  do {                                                                                        \
-    if (STAGES == 3) return launch_ring<KCH_, 3>(g, grid, smem, coo, mean, stream);           \
-    return launch_ring<KCH_, 2>(g, grid, smem, coo, mean, stream);                            \
-  } while (0)
-      if (p.K <= 128) DGS_RING_GEO(1);
-      if (p.K <= 256) DGS_RING_GEO(2);
-      if (p.K <= 512) DGS_RING_GEO(4);
-      DGS_RING_GEO(8);
-#undef DGS_RING_GEO
+      return ring(grid, nullptr);
     }
   }
   int G = 4;
@@ -520,6 +571,7 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
   if (chunk > 4096) chunk = 4096;
   a.chunk = (int)((chunk + kSdBatch - 1) / kSdBatch * kSdBatch);
   a.num_chunks = (int)((p.nnz + a.chunk - 1) / a.chunk);
+  g_last_geo[0] = 0; g_last_geo[1] = 0; g_last_geo[2] = a.chunk;
   ProfileScope prof(3, stream);
   return vec4 ? launch_v<4>(G, a, coo, p.mean != 0 && !coo, mask && !coo, stream)
               : launch_v<1>(G, a, coo, p.mean != 0 && !coo, mask && !coo, stream);

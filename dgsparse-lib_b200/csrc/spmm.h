@@ -62,6 +62,7 @@ struct SddmmProblem {
   float *out = nullptr;         // [nnz]
 };
 cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream);
+void sddmm_last_geometry(int *wpc, int *ctas_per_sm, int *chunk);   // of the calling thread's last sddmm(); ring kernel: wpc > 0
 
 size_t csr2csc_workspace_bytes(int M, int ncols, int64_t nnz);
 // colptr[ncols+1], row[nnz], val_t[nnz] (optional), perm[nnz] (optional): stable transpose

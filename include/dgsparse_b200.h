@@ -50,6 +50,9 @@ int dgs_spmm_last_path(void);
 /* Forget what the library has learnt about the matrices it has seen (which ones may take the row-parallel kernel):
  * the next call on any matrix starts from the row-segment path again.  For tests and benchmarks. */
 void dgs_spmm_forget_graph_notes(void);
+/* Geometry of the calling thread's last SDDMM launch, for tools and tests: warps per CTA and CTAs per SM of the shared-memory
+ * ring kernel (both 0 when the register-staged kernel ran) and the edges per warp / lane group.  Null pointers are skipped. */
+void dgs_sddmm_last_geometry(int *warps_per_cta, int *ctas_per_sm, int *edges_per_warp);
 
 /* The same with K = rows of B (columns of A) stated.  K only sizes the column panels (csrc/spmm.cu pick_panel): when a
  * 64-column panel of B, K x 256 B, would not stay L2-resident the feature axis is processed in narrower panels, one after

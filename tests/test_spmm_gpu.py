@@ -180,6 +180,35 @@ def test_gespmm_descr_api_and_colmajor(oracle, graphs):
     assert_close_f32(Ct.cpu().numpy().T, ref, what="column-major")
 
 
+@pytest.mark.parametrize("N", [7, 33, 64])
+def test_gespmm_colmajor_both_paths_agree(oracle, graphs, N):
+    """transpose_BC = false (src/ge-spmm/csrspmm_non_transpose.cu): the thread-per-element kernel and the row-major kernel
+    between two tiled transposes (what larger products take) give the same column-major C; ragged tile edges (M, K, N not
+    multiples of 32), empty rows and a hub row included."""
+    import dgsparse._lib as L
+    M, Kc = 3001, 2777
+    rowptr, col = graphs.random_csr(M, Kc, 90000, 11, empty_frac=0.15, hub=1)
+    val = graphs.uniform(col.size, 1, 0.5, 1.5)
+    B = graphs.uniform(Kc * N, 2, -1.0, 1.0).reshape(Kc, N)
+    want, want64, T = oracle.spmm(rowptr, col, val, B), oracle.spmm_f64(rowptr, col, val, B), spmm_absref(oracle, rowptr, col, val, B)
+    rp, cc, vv = dev(rowptr), dev(col), dev(val)
+    d = L.SpMatCsrDescr_t(M, Kc, col.size, rp.data_ptr(), cc.data_ptr(), vv.data_ptr())
+    Bt = dev(np.ascontiguousarray(B.T))
+    got = {}
+    try:
+        for path in (0, 1):
+            assert L.lib.dgs_set_option(b"spmm_colmajor", path) == 0
+            Ct = torch.full((N, M), float("nan"), device="cuda")
+            L.lib.gespmmCsrSpMM(d, Bt.data_ptr(), N, Ct.data_ptr(), False, 0)
+            torch.cuda.synchronize()
+            got[path] = Ct.cpu().numpy().T
+            assert_close_f32(got[path], want, want64, what=f"column-major path {path} N={N}", absref=T)
+    finally:
+        L.lib.dgs_set_option(b"spmm_colmajor", -1)
+    # B is left untouched by the transposing path
+    assert np.array_equal(Bt.cpu().numpy(), np.ascontiguousarray(B.T))
+
+
 def test_host_buffer_entry(oracle, graphs):
     """dgs_spmm_csr_host: the HOST-pointer entry bench.py's e2e leg times."""
     import dgsparse._lib as L
