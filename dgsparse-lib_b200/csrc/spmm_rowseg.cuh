@@ -74,7 +74,13 @@ __device__ __forceinline__ SegLayout seg_layout(const SpmmArgs &a) {
   return s;
 }
 
-constexpr int kSpmmThreads = 256;
+// Threads per CTA of the SpMM kernels.  Lane groups never talk to each other, so this only sets the granularity in which an SM's
+// slots are handed out; -DDGS_SPMM_THREADS=64 builds the variant library tools/build_variant.py A/Bs against this one.
+#ifndef DGS_SPMM_THREADS
+#define DGS_SPMM_THREADS 256
+#endif
+constexpr int kSpmmThreads = DGS_SPMM_THREADS;
+constexpr int kSpmmCtaScale = 256 / kSpmmThreads;   // CTAs per SM asked for scale with the CTA size
 constexpr int kBatch = 32;
 
 template <int RED, bool ARG, int VEC>
@@ -105,7 +111,7 @@ constexpr int kStageStride = kBatch + 2;
 // may take the whole register file, it then gave the 8-lane sum kernel 124 registers, and N = 32 ran 12 - 20 % slower at
 // 2 CTAs per SM (reddit-like 0.93 against 0.84 ms, products-like 2.81 against 2.31 ms; tools/exp_ab_r1.py).
 template <int VEC, int G, int RED, int COMP, bool ARG, int U>
-__global__ void __launch_bounds__(kSpmmThreads, (VEC == 4 && G >= 8 && COMP != C_MASK) ? 3 : 0) spmm_rowseg_kernel(const SpmmArgs a) {
+__global__ void __launch_bounds__(kSpmmThreads, (VEC == 4 && G >= 8 && COMP != C_MASK) ? 3 * kSpmmCtaScale : 0) spmm_rowseg_kernel(const SpmmArgs a) {
   constexpr int GPB = kSpmmThreads / G;  // groups (segments) per block
   constexpr int PER = kBatch / G;        // staged entries per lane per batch
   constexpr bool HAS_VAL = (COMP != C_COPY);
