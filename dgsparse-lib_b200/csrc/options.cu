@@ -8,9 +8,9 @@
 namespace dgs {
 namespace {
 const char *kNames[OPT_COUNT] = {"spmm_rowpar", "spmm_panel", "spmm_no_pdl", "spmm_segs", "spmm_chunk_cap", "sddmm_no_ring", "sddmm_stages",
-                                 "sddmm_chunk", "sddmm_wpc", "spconv_ctas", "spmm_colmajor", "sddmm_threads"};
+                                 "sddmm_chunk", "sddmm_wpc", "spconv_ctas", "spmm_colmajor", "sddmm_threads", "sddmm_d1slots"};
 const char *kEnv[OPT_COUNT] = {"DGS_SPMM_ROWPAR", "DGS_SPMM_PANEL", "DGS_SPMM_NO_PDL", "DGS_SPMM_SEGS", "DGS_SPMM_CHUNK_CAP", "DGS_SDDMM_NO_RING",
-                               "DGS_SDDMM_STAGES", "DGS_SDDMM_CHUNK", "DGS_SDDMM_WPC", "DGS_SPCONV_CTAS", "DGS_SPMM_COLMAJOR", "DGS_SDDMM_THREADS"};
+                               "DGS_SDDMM_STAGES", "DGS_SDDMM_CHUNK", "DGS_SDDMM_WPC", "DGS_SPCONV_CTAS", "DGS_SPMM_COLMAJOR", "DGS_SDDMM_THREADS", "DGS_SDDMM_D1SLOTS"};
 std::atomic<int> g_env[OPT_COUNT];
 std::atomic<int> g_override[OPT_COUNT];
 std::once_flag g_once;

@@ -12,11 +12,12 @@
 //   sddmm_wpc        DGS_SDDMM_WPC             warps per CTA of the ring kernel
 //   spconv_ctas      DGS_SPCONV_CTAS           1 .. 3: persistent CTAs per SM of the pipelined spconv kernel (unset: as many as fit)
 //   sddmm_threads    DGS_SDDMM_THREADS         256: 256-thread CTAs for the register-staged SDDMM kernel (unset: 64)
+//   sddmm_d1slots    DGS_SDDMM_D1SLOTS         2 | 4: D1 row slots per ring stage
 //   spmm_colmajor    DGS_SPMM_COLMAJOR         0: gespmmCsrSpMM(transpose_BC = false) takes the thread-per-element kernel instead of transposes around the row-major one
 #pragma once
 
 namespace dgs {
-enum Option { OPT_SPMM_ROWPAR = 0, OPT_SPMM_PANEL, OPT_SPMM_NO_PDL, OPT_SPMM_SEGS, OPT_SPMM_CHUNK_CAP, OPT_SDDMM_NO_RING, OPT_SDDMM_STAGES, OPT_SDDMM_CHUNK, OPT_SDDMM_WPC, OPT_SPCONV_CTAS, OPT_SPMM_COLMAJOR, OPT_SDDMM_THREADS, OPT_COUNT };
+enum Option { OPT_SPMM_ROWPAR = 0, OPT_SPMM_PANEL, OPT_SPMM_NO_PDL, OPT_SPMM_SEGS, OPT_SPMM_CHUNK_CAP, OPT_SDDMM_NO_RING, OPT_SDDMM_STAGES, OPT_SDDMM_CHUNK, OPT_SDDMM_WPC, OPT_SPCONV_CTAS, OPT_SPMM_COLMAJOR, OPT_SDDMM_THREADS, OPT_SDDMM_D1SLOTS, OPT_COUNT };
 int option(Option o);                          // -1 when unset
 int set_option(const char *name, int value);   // value < 0 clears the override (back to the environment); 0 ok, -1 unknown name
 }  // namespace dgs

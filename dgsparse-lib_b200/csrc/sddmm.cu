@@ -37,6 +37,31 @@ struct SddmmArgs {
   int chunk, num_chunks;
 };
 
+// row_of_nnz (common.cuh), by the G lanes of a lane group TOGETHER (all of them call it with the same p; gl = lane index in the group, gmask
+// = the group's lanes of the warp): a G-ary search — every round the lanes probe G evenly spaced row pointers and one ballot
+// picks the sub-range — i.e. log_G(M) dependent loads instead of log_2(M): 4 instead of 18 for a full warp on 169 k rows.
+// The start-of-chunk search is pure latency in front of a chunk's first gather, paid once per chunk.
+template <int G>
+__device__ __forceinline__ int row_of_nnz_group(const int *__restrict__ rowptr, int M, int p, int gl, unsigned gmask) {
+  constexpr int LG = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : 2;
+  static_assert(G == 32 || G == 16 || G == 8 || G == 4, "lane groups of 4, 8, 16 or 32");
+  const int shift = (G == 32) ? 0 : (int)((threadIdx.x & 31u) - (unsigned)gl);
+  constexpr unsigned low = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+  int lo = 0, hi = M;   // smallest idx with rowptr[idx] > p lies in [lo, hi]; rowptr[hi] > p holds throughout (rowptr[M] = nnz > p)
+  while (hi - lo >= G) {
+    const long long span = hi - lo;
+    const int q = lo + (int)((span * (gl + 1)) >> LG);          // probe G - 1 is hi itself
+    const unsigned b = (__ballot_sync(gmask, __ldg(rowptr + q) > p) >> shift) & low;
+    const int f = __ffs(b) - 1;                                  // first probe beyond p (b != 0: the last probe is hi)
+    const int q_prev = lo + (int)((span * f) >> LG);             // probe f - 1 (f = 0: lo, not a probe)
+    hi = lo + (int)((span * (f + 1)) >> LG);
+    lo = (f == 0) ? lo : q_prev + 1;
+  }
+  const int idx = lo + gl;                                       // at most G candidates lo .. hi left
+  const unsigned b = (__ballot_sync(gmask, idx >= hi || __ldg(rowptr + idx) > p) >> shift) & low;
+  return lo + __ffs(b) - 2;
+}
+
 // Reduce NV per-lane partials across the G lanes of a group.  On return the lane whose low
 // log2(G/NV) bits are zero holds, in v[0], the full sum of edge `edge_slot(gl)`.
 template <int G, int NV>
@@ -83,7 +108,7 @@ __global__ void __launch_bounds__(THREADS) sddmm_kernel(const SddmmArgs a) {
 
   int r = 0, row_start = 0, row_end = 0;
   if (!COO) {
-    r = row_of_nnz(a.rowptr, a.M, lo);
+    r = row_of_nnz_group<G>(a.rowptr, a.M, lo, gl, gmask);
     row_start = __ldg(a.rowptr + r);
     row_end = __ldg(a.rowptr + r + 1);
   }
@@ -210,7 +235,7 @@ __global__ void __launch_bounds__(THREADS) sddmm_kernel(const SddmmArgs a) {
 // — lose as well: 0.197 ms for 1 pass, 0.242 for 2 x 128 columns, 0.450 for 4 x 64, tools/exp_sddmm_fsplit.py).
 constexpr int kRgNB = 4;          // edges per batch: one per 8-lane group of the copying warp
 constexpr int kRgBPS = 32 / kRgNB; // batches per 32-edge superbatch
-constexpr int kRgMetaBytes = 2 * kRgBPS * 4 + 2 * 32 * 4;   // two superbatches of packed slots + degrees
+constexpr int kRgMetaBytes = 2 * kRgBPS * 4 + 2 * 32 * 4 + 2 * 32 * 4;   // two superbatches of packed slots + degrees + row indices
 
 __device__ __forceinline__ uint32_t sd_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sd_cp16(uint32_t dst, const void *src) {
@@ -228,6 +253,7 @@ __device__ __forceinline__ const char *sd_shfl_ptr(const char *p, int src_lane) 
 struct SddmmRingArgs {
   SddmmArgs a;
   int wpc;             // warps per CTA
+  int nd;              // D1 row slots per stage (2 or 4); a batch's further distinct D1 rows are read from global by the consumer
   uint32_t slot_bytes; // K*4 rounded up to 128
   uint32_t warp_bytes; // shared memory per warp
 };
@@ -242,12 +268,15 @@ __global__ void __launch_bounds__(512, 1) sddmm_ring_kernel(const SddmmRingArgs 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = lane >> 3, ql = lane & 7;
   const uint32_t rowbytes = (uint32_t)a.K * 4u;
-  // per-warp carve-up: [STAGES][2*NB] row slots | packed D1 slots per batch [2][BPS] | degree per edge [2][32]
+  // per-warp carve-up: [STAGES][NB + nd] row slots | packed D1 slots per batch [2][BPS] | degree per edge [2][32] | row per edge [2][32]
   uint8_t *wbase = sd_smem + (size_t)warp * g.warp_bytes;
   const uint32_t rows_u32 = sd_smem_u32(wbase);
-  const uint32_t stage_bytes = 2u * NB * g.slot_bytes;
+  constexpr bool OVF = KCH <= 4;   // K > 512: always four D1 slots (the overflow path costs the 8-chunk consumer its registers)
+  const int nd = OVF ? g.nd : NB;
+  const uint32_t stage_bytes = (uint32_t)(NB + nd) * g.slot_bytes;
   int *s_slots = reinterpret_cast<int *>(wbase + (size_t)STAGES * stage_bytes);
   int *s_deg = s_slots + 2 * BPS;
+  int *s_rowidx = s_deg + 2 * 32;
   uint64_t pol_stream;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
 
@@ -257,7 +286,7 @@ __global__ void __launch_bounds__(512, 1) sddmm_ring_kernel(const SddmmRingArgs 
   const int hi = (a.nnz - lo <= a.chunk) ? a.nnz : lo + a.chunk;
   const int nb_total = (hi - lo + NB - 1) / NB;
 
-  int r_hint = COO ? 0 : row_of_nnz(a.rowptr, a.M, lo);   // row of the superbatch's first edge (uniform)
+  int r_hint = COO ? 0 : row_of_nnz_group<32>(a.rowptr, a.M, lo, lane, 0xffffffffu);   // row of the chunk's first edge (uniform)
   bool in_k[KCH];
 #pragma unroll
   for (int j = 0; j < KCH; j++) in_k[j] = FULLK || (lane + 32 * j) * 4 < a.K;
@@ -295,6 +324,7 @@ __global__ void __launch_bounds__(512, 1) sddmm_ring_kernel(const SddmmRingArgs 
       s_slots[(sb & 1) * BPS + lane / NB] = (s1 << 4) | (s2 << 8) | (s3 << 12);
     }
     if (MEAN) s_deg[(sb & 1) * 32 + lane] = deg;
+    if (nd < NB) s_rowidx[(sb & 1) * 32 + lane] = rr;   // for the consumer's global read of a batch's third / fourth D1 row
     if (!COO) r_hint = __shfl_sync(0xffffffffu, rr, 31);   // rows are monotone: the next superbatch searches from here
   };
 
@@ -311,8 +341,9 @@ __global__ void __launch_bounds__(512, 1) sddmm_ring_kernel(const SddmmRingArgs 
 #pragma unroll
       for (int i = 0; i < SEGS; i++)
         if (FULLK || i * 128u + ql * 16u < rowbytes) sd_cp16(dst2 + 128u * i, p2 + 128 * i);
-      if ((gb >> q) & 1u) {
-        const uint32_t dst1 = sbase + (uint32_t)(NB + __popc(gb & ((2u << q) - 1u)) - 1) * g.slot_bytes;
+      const int slot1 = __popc(gb & ((2u << q) - 1u)) - 1;   // D1 slot of edge q: new flags among edges 0 .. q, minus one
+      if (((gb >> q) & 1u) && slot1 < nd) {
+        const uint32_t dst1 = sbase + (uint32_t)(NB + slot1) * g.slot_bytes;
 #pragma unroll
         for (int i = 0; i < SEGS; i++)
           if (FULLK || i * 128u + ql * 16u < rowbytes) sd_cp16_hint(dst1 + 128u * i, p1 + 128 * i, pol_stream);
@@ -347,10 +378,18 @@ __global__ void __launch_bounds__(512, 1) sddmm_ring_kernel(const SddmmRingArgs 
     for (int e = 0; e < NB; e++) {
       const int d1 = (packed >> (4 * e)) & 15;
       if (e == 0 || d1 != ((packed >> (4 * (e - 1))) & 15)) {   // uniform: the D1 row changes with this edge
-        const float4 *xr = reinterpret_cast<const float4 *>(srows + (size_t)(NB + d1) * g.slot_bytes);
+        if (!OVF || d1 < nd) {
+          const float4 *xr = reinterpret_cast<const float4 *>(srows + (size_t)(NB + d1) * g.slot_bytes);
 #pragma unroll
-        for (int j = 0; j < KCH; j++)
-          if (in_k[j]) x[j] = xr[lane + 32 * j];
+          for (int j = 0; j < KCH; j++)
+            if (in_k[j]) x[j] = xr[lane + 32 * j];
+        } else {   // rare (nd = 2: three or four distinct rows among four consecutive edges): no ring slot, read the row from global
+          const int rr = s_rowidx[((b / BPS) & 1) * 32 + (b % BPS) * NB + e];
+          const float4 *xr = reinterpret_cast<const float4 *>(a.D1 + (size_t)rr * a.ld1);
+#pragma unroll
+          for (int j = 0; j < KCH; j++)
+            if (in_k[j]) x[j] = __ldg(xr + lane + 32 * j);
+        }
       }
       float acc = 0.0f;
 #pragma unroll
@@ -491,7 +530,16 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
     // K = 256 32.4 -> 26.8 us (the last line that trailed the reference's kernel, 29.1 us).
     int STAGES = 2;
     if (option(OPT_SDDMM_STAGES) == 3) STAGES = 3;
-    g.warp_bytes = (uint32_t)STAGES * 2u * kRgNB * g.slot_bytes + (uint32_t)kRgMetaBytes;
+    // D1 slots per stage: four consecutive edges of a CSR rarely touch more than two rows, so two slots (and a global read by
+    // the consumer for a batch's third / fourth row) leave room for a third more rings per SM (16 instead of 12 at K = 256,
+    // 8 instead of 6 at K = 512).  Measured (tools/exp_sddmm_ring.py --d1, profiles/r02_exp_sddmm_ring_d1.jsonl): level on
+    // the arxiv-like graph (the kernel is not short of rings there), 10 - 18 % faster on the two fixtures at K >= 256, where
+    // more resident warps mean fewer waves (p2p-Gnutella31 K = 256 / 512 24.3 / 50.0 -> 21.0 / 43.3 us).  COO rows need not be
+    // sorted and matrices of one-edge rows would take the global read on every batch: both keep four slots.
+    g.nd = (!coo && p.nnz >= 2 * (int64_t)p.M) ? 2 : kRgNB;
+    if (option(OPT_SDDMM_D1SLOTS) == 2 || option(OPT_SDDMM_D1SLOTS) == 4) g.nd = option(OPT_SDDMM_D1SLOTS);
+    if (p.K > 512) g.nd = kRgNB;   // the 8-chunk instantiations are compiled without the overflow path
+    g.warp_bytes = (uint32_t)STAGES * (uint32_t)(kRgNB + g.nd) * g.slot_bytes + (uint32_t)kRgMetaBytes;
     g.warp_bytes = (g.warp_bytes + 127u) & ~127u;
     int wpc = g.warp_bytes <= 220u * 1024u ? 1 : 0;
     if (option(OPT_SDDMM_WPC) >= 1 && option(OPT_SDDMM_WPC) <= 16 && (size_t)option(OPT_SDDMM_WPC) * g.warp_bytes <= 220u * 1024u)
@@ -521,14 +569,14 @@ cudaError_t sddmm(const SddmmProblem &p, cudaStream_t stream) {
       if (ctas_per_sm < 1) ctas_per_sm = 1;
       const int64_t resident_warps = (int64_t)device_sm_count() * wpc * ctas_per_sm;
       // Edges per warp.  Large inputs: ~6 chunks per resident warp for dynamic balance.  When that would cut chunks shorter
-      // than ~144 edges (arxiv-like: 1.17 M edges on 1 924 .. 4 144 resident warps) the per-chunk costs — the row search, the
-      // ring's fill and drain — show: take chunks of ~144 edges instead, sized so that the grid is a whole number of waves
-      // of resident warps (tools/exp_sddmm_ring.py --chunks, profiles/r02_exp_sddmm_ring_chunks.jsonl: arxiv-like K = 64
-      // 48 -> 96 .. 160 edges 0.0777 -> 0.072 ms, K = 128 56 -> 128 .. 192 0.0906 -> 0.084 ms, K = 256 / 512 flat between 64 and
-      // 220; 256 and more lose again, and a ragged last wave costs ~7 %).
+      // than ~112 edges (arxiv-like: 1.17 M edges on 1 184 .. 4 292 resident warps) the per-chunk costs — the row search, the
+      // ring's fill and drain — show: take chunks of at most ~112 edges instead, sized so that the grid is a whole number of
+      // waves of resident warps (tools/exp_sddmm_ring.py --chunks / --d1, profiles/r02_exp_sddmm_ring_chunks.jsonl,
+      // r02_exp_sddmm_ring_d1.jsonl: arxiv-like K = 64 48 -> 96 edges 0.0777 -> 0.072 ms, K = 128 56 -> 92 0.0906 -> 0.075 ms,
+      // K = 256 / 512 flat between 64 and 220; 256 and more lose again, and a ragged last wave costs ~7 %).
       int64_t chunk = (p.nnz + resident_warps * 6 - 1) / (resident_warps * 6);
-      if (chunk < 144) {
-        int64_t waves = (p.nnz + resident_warps * 72) / (resident_warps * 144);   // nearest whole number of waves
+      if (chunk < 112) {
+        int64_t waves = (p.nnz + resident_warps * 112 - 1) / (resident_warps * 112);
         if (waves < 1) waves = 1;
         chunk = (p.nnz + resident_warps * waves - 1) / (resident_warps * waves);
       }

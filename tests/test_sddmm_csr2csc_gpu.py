@@ -67,6 +67,49 @@ def test_sddmm_widths(K, oracle, graphs, Kd):
                      absref=sddmm_absref(oracle, rowptr, col, D1, D2)[perm])
 
 
+@pytest.mark.parametrize("Kd", [64, 100, 128, 256, 384, 512])
+@pytest.mark.parametrize("shape", ["deg1", "deg1to3", "mixed"])
+def test_sddmm_ring_two_d1_slots(K, oracle, graphs, Kd, shape):
+    """The ring kernel with TWO D1 slots per stage (what CSR inputs with >= 4 edges per row get): a batch's third / fourth distinct
+    row is read from global by the consumer.  Matrices made of very short rows take that path on most batches; the result must be
+    bit-identical to the four-slot ring (same dot, only the source of the D1 row differs) and match the oracle."""
+    import ctypes
+
+    import dgsparse._lib as L
+    rng = np.random.default_rng(7)
+    M, Kc = 6000, 3000
+    if shape == "deg1":
+        deg = np.ones(M, np.int64)
+    elif shape == "deg1to3":
+        deg = rng.integers(0, 4, M)
+    else:   # runs of one-edge rows between hub rows and empty stretches
+        deg = rng.integers(0, 3, M)
+        deg[::97] = rng.integers(40, 300, deg[::97].size)
+        deg[1000:1200] = 0
+    rowptr = np.zeros(M + 1, np.int32)
+    rowptr[1:] = np.cumsum(deg)
+    col = rng.integers(0, Kc, int(rowptr[-1])).astype(np.int32)
+    D1 = graphs.uniform(M * Kd, 1, -1, 1).reshape(M, Kd)
+    D2 = graphs.uniform(Kc * Kd, 2, -1, 1).reshape(Kc, Kd)
+    got = {}
+    try:
+        for nd in (2, 4):
+            assert L.lib.dgs_set_option(b"sddmm_d1slots", nd) == 0
+            assert L.lib.dgs_set_option(b"sddmm_no_ring", 0) == 0     # the ring also for K = 64 on a small input
+            for mean in (False, True):
+                got[nd, mean] = K.sddmm_csr(dev(rowptr), dev(col), dev(D1), dev(D2), mean=mean).cpu().numpy()[0]
+                w = ctypes.c_int()
+                L.lib.dgs_sddmm_last_geometry(ctypes.byref(w), None, None)
+                assert w.value >= 1, "ring kernel expected"
+    finally:
+        L.lib.dgs_set_option(b"sddmm_d1slots", -1)
+        L.lib.dgs_set_option(b"sddmm_no_ring", -1)
+    for mean in (False, True):
+        assert np.array_equal(got[2, mean], got[4, mean]), f"two vs four D1 slots differ (mean={mean})"
+        assert_close_f32(got[2, mean], oracle.sddmm_csr(rowptr, col, D1, D2, mean), oracle.sddmm_csr(rowptr, col, D1, D2, mean, f64=True),
+                         what=f"two D1 slots K={Kd} {shape} mean={mean}", absref=sddmm_absref(oracle, rowptr, col, D1, D2, mean))
+
+
 @pytest.mark.parametrize("Kd", [8, 30, 64, 256])
 @pytest.mark.parametrize("nnz_shape", ["1", "3", "7", "9", "hub0_tail", "hub0_33"])
 def test_sddmm_tiny_and_hub_row0(K, oracle, graphs, Kd, nnz_shape):

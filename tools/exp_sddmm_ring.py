@@ -21,12 +21,13 @@ from tools.bench_vs_ref import timeit  # noqa: E402
 
 graphs.build()
 quick = "--quick" in sys.argv
+d1_mode = "--d1" in sys.argv              # two vs four D1 slots per ring stage (x a few chunk lengths)
 chunks_mode = "--chunks" in sys.argv      # sweep the edges per warp at the library's own CTA geometry instead of the CTA size
 st = torch.cuda.current_stream().cuda_stream
 
 
 def setopt(**kw):
-    for k in ("sddmm_stages", "sddmm_wpc", "sddmm_chunk", "sddmm_no_ring"):
+    for k in ("sddmm_stages", "sddmm_wpc", "sddmm_chunk", "sddmm_no_ring", "sddmm_d1slots"):
         L.lib.dgs_set_option(k.encode(), int(kw.get(k, -1)))
 
 
@@ -49,7 +50,12 @@ for gname, (rowptr, col), widths, reps in cases:
         run = lambda: L.lib.dgs_sddmm_csr(M, Kd, nnz, rp.data_ptr(), cc.data_ptr(), D1.data_ptr(), Kd, D2.data_ptr(), Kd, None, 0,
                                           out.data_ptr(), st)
         settings = [dict()]
-        if chunks_mode:
+        if d1_mode:
+            for nd in (4, 2):
+                settings.append(dict(sddmm_d1slots=nd))
+                for c in (96, 144, 192, 256):
+                    settings.append(dict(sddmm_d1slots=nd, sddmm_chunk=c))
+        elif chunks_mode:
             for c in (32, 48, 64, 96, 128, 160, 192, 256, 320, 384, 512, 768, 1024):
                 settings.append(dict(sddmm_chunk=c))
             if Kd == 64:
@@ -65,7 +71,7 @@ for gname, (rowptr, col), widths, reps in cases:
             setopt(**s)
             t = timeit(run, reps)
             geo = geometry()
-            key = (s.get("sddmm_stages", 2), geo["wpc"], geo["edges_per_warp"], s.get("sddmm_no_ring", -1))
+            key = (s.get("sddmm_stages", 2), geo["wpc"], geo["ctas_per_sm"], geo["edges_per_warp"], s.get("sddmm_no_ring", -1), s.get("sddmm_d1slots", -1))
             if s and key in seen:      # the override did not fit and the library fell back to a geometry already timed
                 continue
             seen.add(key)
