@@ -52,14 +52,14 @@ __device__ __forceinline__ int row_of_nnz_group(const int *__restrict__ rowptr, 
     const long long span = hi - lo;
     const int q = lo + (int)((span * (gl + 1)) >> LG);          // probe G - 1 is hi itself
     const unsigned b = (__ballot_sync(gmask, __ldg(rowptr + q) > p) >> shift) & low;
-    const int f = __ffs(b) - 1;                                  // first probe beyond p (b != 0: the last probe is hi)
+    const int f = b ? __ffs(b) - 1 : G - 1;                      // first probe beyond p (b != 0 for a valid CSR: the last probe is hi)
     const int q_prev = lo + (int)((span * f) >> LG);             // probe f - 1 (f = 0: lo, not a probe)
     hi = lo + (int)((span * (f + 1)) >> LG);
     lo = (f == 0) ? lo : q_prev + 1;
   }
   const int idx = lo + gl;                                       // at most G candidates lo .. hi left
   const unsigned b = (__ballot_sync(gmask, idx >= hi || __ldg(rowptr + idx) > p) >> shift) & low;
-  return lo + __ffs(b) - 2;
+  return max(0, min(M - 1, lo + __ffs(b) - 2));   // the clamp only matters for an inconsistent CSR (nnz beyond rowptr[M])
 }
 
 // Reduce NV per-lane partials across the G lanes of a group.  On return the lane whose low
