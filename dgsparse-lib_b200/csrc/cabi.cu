@@ -206,6 +206,19 @@ int dgs_sm_count(void) { return dgs::device_sm_count(); }
 int dgs_spmm_last_path(void) { return dgs::spmm_last_path(); }
 int dgs_set_option(const char *name, int value) { return dgs::set_option(name, value); }
 void dgs_spmm_forget_graph_notes(void) { dgs::spmm_forget_graph_notes(); }
+int dgs_legacy_scratch_release(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(e, "dgs_legacy_scratch_release");
+  if (dev < 0 || dev >= 64) return fail(cudaErrorInvalidDevice, "dgs_legacy_scratch_release");
+  std::lock_guard<std::mutex> lk(g_mu);
+  Scratch &s = g_scratch[dev];
+  if (s.ptr == nullptr) return 0;
+  if ((e = cudaStreamSynchronize(0)) != cudaSuccess) return fail(e, "dgs_legacy_scratch_release(sync)");
+  e = cudaFree(s.ptr);
+  s.ptr = nullptr; s.bytes = 0;
+  return ok_or(e, "dgs_legacy_scratch_release(free)");
+}
 void dgs_sddmm_last_geometry(int *warps_per_cta, int *ctas_per_sm, int *edges_per_warp) {
   dgs::sddmm_last_geometry(warps_per_cta, ctas_per_sm, edges_per_warp);
 }

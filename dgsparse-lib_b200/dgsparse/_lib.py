@@ -28,6 +28,7 @@ SIGNATURES = {
     "dgs_spmm_last_path": (_i32, []),
     "dgs_spmm_forget_graph_notes": (None, []),
     "dgs_sddmm_last_geometry": (None, [_vp, _vp, _vp]),
+    "dgs_legacy_scratch_release": (_i32, []),
     "dgs_set_option": (_i32, [ctypes.c_char_p, _i32]),
     "dgs_spmm_csr_k": (_i32, [_i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _sz, _vp]),
     "dgs_spmm_csr_multi": (_i32, [_i32, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _sz, _vp]),

@@ -50,6 +50,11 @@ int dgs_spmm_last_path(void);
 /* Forget what the library has learnt about the matrices it has seen (which ones may take the row-parallel kernel):
  * the next call on any matrix starts from the row-segment path again.  For tests and benchmarks. */
 void dgs_spmm_forget_graph_notes(void);
+/* The legacy entry points of dgsparse.h take no workspace argument: the library keeps ONE grow-only device scratch per device for
+ * them (segment partials; for column-major gespmmCsrSpMM also the transposed copies of B and C), used on stream 0 only.  This
+ * waits for stream 0 of the current device and frees that scratch; the next legacy call allocates what it needs again.
+ * Returns 0 or a cudaError_t value. */
+int dgs_legacy_scratch_release(void);
 /* Geometry of the calling thread's last SDDMM launch, for tools and tests: warps per CTA and CTAs per SM of the shared-memory
  * ring kernel (both 0 when the register-staged kernel ran) and the edges per warp / lane group.  Null pointers are skipped. */
 void dgs_sddmm_last_geometry(int *warps_per_cta, int *ctas_per_sm, int *edges_per_warp);

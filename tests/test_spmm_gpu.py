@@ -207,6 +207,15 @@ def test_gespmm_colmajor_both_paths_agree(oracle, graphs, N):
         L.lib.dgs_set_option(b"spmm_colmajor", -1)
     # B is left untouched by the transposing path
     assert np.array_equal(Bt.cpu().numpy(), np.ascontiguousarray(B.T))
+    # the legacy scratch (segment partials + the transposed copies) can be handed back and is re-allocated on demand
+    free0 = torch.cuda.mem_get_info()[0]
+    assert L.lib.dgs_legacy_scratch_release() == 0
+    assert torch.cuda.mem_get_info()[0] >= free0
+    assert L.lib.dgs_legacy_scratch_release() == 0          # nothing held: still fine
+    Ct = torch.full((N, M), float("nan"), device="cuda")
+    L.lib.gespmmCsrSpMM(d, Bt.data_ptr(), N, Ct.data_ptr(), False, 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(Ct.cpu().numpy().T, got[1])
 
 
 def test_host_buffer_entry(oracle, graphs):
