@@ -18,7 +18,10 @@ output panel is then made available on every rank, in one of two ways:
   mode="nccl"  the baseline: local SpMM, then one ncclAllGather of the [M, n_local] panel into a
                panel-major [world, M, n_local] buffer (panels_to_row_major() permutes when needed).
 
-No reduction is involved, so results are bit-identical to the single-GPU kernel.
+No reduction is involved, so every rank's panel is bit-identical to the single-GPU kernel run on that panel.  (One single-GPU
+launch over the FULL width is a different launch: the kernel cuts the nnz stream into segments according to the launch's
+number of column panels, and a row cut by a segment boundary is then summed in a different order — equal to fp32 round-off
+for sum / mean, still bit-identical for max / min.  tests/mgpu_worker.py checks both statements.)
 
 Output buffering (peer / mcast): remote ranks store into this rank's C, and the only cross-rank synchronisation is the
 completion barrier AFTER the stores.  C is therefore DOUBLE-BUFFERED and alternates per call: step k+1 writes the buffer

@@ -26,10 +26,22 @@ def main():
     Bfull = graphs.uniform(M * n_local * world, 2, -1, 1).reshape(M, n_local * world)
     rp, cc, vv = (torch.from_numpy(a).to(dev) for a in (rowptr, col, val))
     Bf = torch.from_numpy(Bfull).to(dev)
-    ref = K.spmm(rp, cc, vv, Bf)                                   # single-GPU kernel on the full width
+    # The oracle of the exchange: the single-GPU kernel on every rank's column panel, side by side.  No reduction crosses ranks,
+    # so the sharded result must equal it BIT FOR BIT.  (The single-GPU kernel on the full width is a different launch: how
+    # the nnz stream is cut into segments depends on the number of column panels of the launch, and a row cut by a segment
+    # boundary is summed in a different order — equal to fp32 round-off for sum, bit-identical for max, checked below.)
+    def per_panel(Bmat, reduce=L.SUM):
+        return torch.cat([K.spmm(rp, cc, vv, Bmat[:, r * n_local:(r + 1) * n_local].contiguous(), reduce, L.MUL)
+                          for r in range(world)], dim=1)
+    ref = per_panel(Bf)
     B_local = Bf[:, rank * n_local:(rank + 1) * n_local].contiguous()
     for reduce in (L.SUM, L.MAX):
-        refr = K.spmm(rp, cc, vv, Bf, reduce, L.MUL)
+        refr = per_panel(Bf, reduce)
+        full = K.spmm(rp, cc, vv, Bf, reduce, L.MUL)               # one launch over the full width
+        if reduce == L.MAX:
+            assert torch.equal(full, refr)
+        else:
+            assert torch.allclose(full, refr, rtol=1e-5, atol=1e-5)
         for mode in ("mcast", "peer", "nccl"):
             op = ColumnShardedSpMM(rp, cc, vv, n_local, reduce=reduce, mode=mode)
             for it in range(3):
@@ -63,7 +75,7 @@ def main():
             C = out if op.mode in ("peer", "mcast") else panels_to_row_major(out)
             stash.append(C.clone())
         torch.cuda.synchronize()
-        ok = all(torch.equal(stash[k], K.spmm(rp, cc, vv, (Bf + float(k)).contiguous())) for k in range(steps))
+        ok = all(torch.equal(stash[k], per_panel((Bf + float(k)).contiguous())) for k in range(steps))
         flag = torch.tensor([int(ok)], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
